@@ -1,0 +1,37 @@
+// Shared helpers for the sm_100a MAGI kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/magi_b200.h"
+
+#define MAGI_CHAINS_PER_CTA 8   // chains of one dataset processed together (DMMA n = 8)
+#define MAGI_FULL_MASK 0xffffffffu
+
+static inline int magi_cuda_status(cudaError_t e) { return e == cudaSuccess ? MAGI_OK : MAGI_ERR_CUDA + (int)e; }
+
+// rows/cols of the packed matrices are padded to a multiple of 8 doubles (64 B)
+__host__ __device__ static inline int magi_pad8(int n) { return (n + 7) & ~7; }
+
+// packed layout: [B][D][3][np][np], slot 0 = sym(C^-1), 1 = m, 2 = sym(K^-1); padding is zero.
+__host__ __device__ static inline size_t magi_packed_mat_elems(int n) {
+  return (size_t)magi_pad8(n) * (size_t)magi_pad8(n);
+}
+
+// softplus / sigmoid in the overflow-safe form; equals log(1+exp(z)) (magi_v2.py:318-319) to
+// rounding wherever the naive form is finite.
+__device__ __forceinline__ double magi_softplus(double z) { return fmax(z, 0.0) + log1p(exp(-fabs(z))); }
+__device__ __forceinline__ double magi_sigmoid(double z) {
+  double e = exp(-fabs(z));
+  return z >= 0.0 ? 1.0 / (1.0 + e) : e / (1.0 + e);
+}
+
+__device__ __forceinline__ double magi_shfl_xor(double v, int m) { return __shfl_xor_sync(MAGI_FULL_MASK, v, m); }
+__device__ __forceinline__ double magi_shfl_down(double v, int d) { return __shfl_down_sync(MAGI_FULL_MASK, v, d); }
+
+__device__ __forceinline__ double magi_warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += magi_shfl_xor(v, o);
+  return v;
+}

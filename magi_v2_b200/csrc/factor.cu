@@ -1,0 +1,267 @@
+// (2) factorise + derive: from the Matern blocks (C, C', C'') of each (dataset, component) to
+// the matrices the sampler needs,  C^-1,  m = C' C^-1,  K^-1 with K = C'' - m C'^T,  banded.
+// Replaces magi_v2.py:818-820 + :126-128 (three SVD pseudo-inverses and two GEMMs per
+// component on the CPU) + :271-274 (band_part).
+//
+// Design: a persistent grid; each CTA takes whole matrices and runs a blocked, GEMM-based FP64
+// "mini-LAPACK" on them in global memory (operands stay L2-resident: <= 13 MB per matrix at
+// n = 1281) with 64x64 shared-memory tiles:
+//   left-looking blocked Cholesky (diagonal 64x64 blocks factorised and inverted in shared memory)
+//   -> blocked triangular inverse -> A^-1 = L^-T L^-1 -> GEMMs for m and K -> same for K.
+// Everything but the 64x64 diagonal work is the CTA-level GEMM below.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kNB = 64;        // block size = GEMM tile size
+constexpr int kKC = 16;        // GEMM k-chunk
+constexpr int kFT = 256;       // threads per CTA
+constexpr int kLd = kNB + 1;   // padded leading dimension of shared tiles
+
+struct FactorSmem {
+  double a[kKC][kLd];
+  double b[kKC][kLd];
+  double d[kNB][kLd];   // diagonal block
+  double di[kNB][kLd];  // its inverse
+  int info;
+};
+
+// C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C   (all 256 threads; C row-major with ldc).
+// op(A)(i,k) = A[i*rsA + k*csA], op(B)(k,j) = B[k*rsB + j*csB]; one of each stride pair is 1.
+// C may alias A when N <= 64 (each 64-row strip of A is fully read before the strip is stored).
+__device__ void cta_gemm(int M, int N, int K, double alpha, const double* A, long rsA, long csA, const double* B,
+                         long rsB, long csB, double beta, double* C, long ldc, FactorSmem& sm) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int m0 = 0; m0 < M; m0 += kNB) {
+    for (int n0 = 0; n0 < N; n0 += kNB) {
+      double acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+      for (int k0 = 0; k0 < K; k0 += kKC) {
+#pragma unroll
+        for (int e = tid; e < kNB * kKC; e += kFT) {
+          int kk, i;
+          if (csA == 1) { kk = e & (kKC - 1); i = e >> 4; } else { i = e & (kNB - 1); kk = e >> 6; }
+          const int gi = m0 + i, gk = k0 + kk;
+          sm.a[kk][i] = (gi < M && gk < K) ? A[gi * rsA + gk * csA] : 0.0;
+          int j;
+          if (csB == 1) { j = e & (kNB - 1); kk = e >> 6; } else { kk = e & (kKC - 1); j = e >> 4; }
+          const int gj = n0 + j;
+          const int gk2 = k0 + kk;
+          sm.b[kk][j] = (gj < N && gk2 < K) ? B[gk2 * rsB + gj * csB] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kKC; ++kk) {
+          double av[4], bv[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) av[r] = sm.a[kk][ty * 4 + r];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) bv[c] = sm.b[kk][tx * 4 + c];
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int gi = m0 + ty * 4 + r;
+        if (gi >= M) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int gj = n0 + tx * 4 + c;
+          if (gj >= N) continue;
+          double* p = C + gi * ldc + gj;
+          *p = beta == 0.0 ? alpha * acc[r][c] : fma(alpha, acc[r][c], beta * *p);
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// In shared memory: Cholesky of the nb x nb block sm.d (lower), then sm.di = inverse of the factor.
+// Non-positive pivot: records (base + column + 1) in sm.info (first failure only).
+__device__ void smem_potrf_trtri(FactorSmem& sm, int nb, int base) {
+  const int tid = threadIdx.x;
+  for (int j = 0; j < nb; ++j) {
+    if (tid == 0) {
+      const double p = sm.d[j][j];
+      if (!(p > 0.0) && sm.info == 0) sm.info = base + j + 1;
+      sm.d[j][j] = sqrt(p);
+    }
+    __syncthreads();
+    const double inv = 1.0 / sm.d[j][j];
+    for (int i = j + 1 + tid; i < nb; i += kFT) sm.d[i][j] *= inv;
+    __syncthreads();
+    // trailing update of the lower triangle: d[i][k] -= d[i][j] d[k][j],  j < k <= i < nb
+    const int rem = nb - j - 1;
+    for (int e = tid; e < rem * rem; e += kFT) {
+      const int i = j + 1 + e / rem, k = j + 1 + e % rem;
+      if (k <= i) sm.d[i][k] = fma(-sm.d[i][j], sm.d[k][j], sm.d[i][k]);
+    }
+    __syncthreads();
+  }
+  // inverse of the lower-triangular factor, one column per thread (forward substitution)
+  for (int e = tid; e < kNB * kNB; e += kFT) sm.di[e / kNB][e % kNB] = 0.0;
+  __syncthreads();
+  if (tid < nb) {
+    const int c = tid;
+    sm.di[c][c] = 1.0 / sm.d[c][c];
+    for (int i = c + 1; i < nb; ++i) {
+      double s = 0.0;
+      for (int k = c; k < i; ++k) s = fma(sm.d[i][k], sm.di[k][c], s);
+      sm.di[i][c] = -s / sm.d[i][i];
+    }
+  }
+  __syncthreads();
+}
+
+// A (n x n, lower triangle used) -> L (in Lf, lower; upper part left as is) and Linv = L^-1 (full
+// n x n, upper part zero).  T: scratch kNB x n.  All in global memory.
+__device__ void cta_chol_inverse(double* Lf, double* Linv, double* T, int n, FactorSmem& sm) {
+  const int tid = threadIdx.x;
+  for (size_t e = tid; e < (size_t)n * n; e += kFT) Linv[e] = 0.0;
+  __syncthreads();
+  const int nblk = (n + kNB - 1) / kNB;
+  for (int k = 0; k < nblk; ++k) {
+    const int c0 = k * kNB, nb = min(kNB, n - c0);
+    // left-looking update of block column k:  A[c0:n, c0:c0+nb] -= L[c0:n, 0:c0] L[c0:c0+nb, 0:c0]^T
+    if (k > 0) cta_gemm(n - c0, nb, c0, -1.0, Lf + (size_t)c0 * n, n, 1, Lf + (size_t)c0 * n, 1, n, 1.0,
+                        Lf + (size_t)c0 * n + c0, n, sm);
+    for (int e = tid; e < kNB * kNB; e += kFT) {
+      const int i = e / kNB, j = e % kNB;
+      sm.d[i][j] = (i < nb && j < nb && j <= i) ? Lf[(size_t)(c0 + i) * n + c0 + j] : (i == j ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    smem_potrf_trtri(sm, nb, c0);
+    for (int e = tid; e < nb * nb; e += kFT) {
+      const int i = e / nb, j = e % nb;
+      if (j <= i) {
+        Lf[(size_t)(c0 + i) * n + c0 + j] = sm.d[i][j];
+        Linv[(size_t)(c0 + i) * n + c0 + j] = sm.di[i][j];
+      }
+    }
+    __syncthreads();
+    // panel below the diagonal block:  L[r, blk] = A[r, blk] * inv(L_kk)^T   (in place, N = nb <= 64)
+    const int r0 = c0 + nb;
+    if (r0 < n)
+      cta_gemm(n - r0, nb, nb, 1.0, Lf + (size_t)r0 * n + c0, n, 1, Linv + (size_t)c0 * n + c0, 1, n, 0.0,
+               Lf + (size_t)r0 * n + c0, n, sm);
+  }
+  // blocked triangular inverse, block row by block row:
+  //   Linv[i, 0:c0] = -Linv_ii * ( L[i, 0:c0] * Linv[0:c0, 0:c0] )
+  for (int i = 1; i < nblk; ++i) {
+    const int c0 = i * kNB, nb = min(kNB, n - c0);
+    cta_gemm(nb, c0, c0, 1.0, Lf + (size_t)c0 * n, n, 1, Linv, n, 1, 0.0, T, n, sm);
+    cta_gemm(nb, c0, nb, -1.0, Linv + (size_t)c0 * n + c0, n, 1, T, n, 1, 0.0, Linv + (size_t)c0 * n, n, sm);
+  }
+}
+
+__global__ void __launch_bounds__(kFT)
+factor_kernel(const double* __restrict__ C, const double* __restrict__ Cp, const double* __restrict__ Cpp, int nmat,
+              int n, int band, double jitter, double* __restrict__ Cinv, double* __restrict__ m,
+              double* __restrict__ Kinv, double* __restrict__ Kout, int32_t* __restrict__ info, double* ws) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  FactorSmem& sm = *reinterpret_cast<FactorSmem*>(smraw);
+  const int tid = threadIdx.x;
+  const size_t nn = (size_t)n * n;
+  double* Lf = ws + (size_t)blockIdx.x * (2 * nn + (size_t)kNB * n);
+  double* Linv = Lf + nn;
+  double* T = Linv + nn;
+  for (int mat = blockIdx.x; mat < nmat; mat += gridDim.x) {
+    const double* c = C + mat * nn;
+    const double* cp = Cp + mat * nn;
+    const double* cpp = Cpp + mat * nn;
+    double* ci = Cinv + mat * nn;
+    double* mo = m + mat * nn;
+    double* ki = Kinv + mat * nn;
+    if (tid == 0) sm.info = 0;
+    for (size_t e = tid; e < nn; e += kFT) {
+      const int i = (int)(e / n), j = (int)(e % n);
+      Lf[e] = c[e] + (i == j ? jitter : 0.0);
+    }
+    __syncthreads();
+    cta_chol_inverse(Lf, Linv, T, n, sm);
+    const int infoC = sm.info;
+    __syncthreads();
+    if (tid == 0) sm.info = 0;
+    // C^-1 = Linv^T Linv
+    cta_gemm(n, n, n, 1.0, Linv, 1, n, Linv, n, 1, 0.0, ci, n, sm);
+    // m = C' C^-1
+    cta_gemm(n, n, n, 1.0, cp, n, 1, ci, n, 1, 0.0, mo, n, sm);
+    // K = C'' - m C'^T   (held in the Kinv buffer until factorised)
+    for (size_t e = tid; e < nn; e += kFT) ki[e] = cpp[e];
+    __syncthreads();
+    cta_gemm(n, n, n, -1.0, mo, n, 1, cp, 1, n, 1.0, ki, n, sm);
+    // symmetrise K (the factorisation reads the lower triangle), keep a copy if asked for
+    for (size_t e = tid; e < nn; e += kFT) {
+      const int i = (int)(e / n), j = (int)(e % n);
+      if (j <= i) {
+        const double v = 0.5 * (ki[e] + ki[(size_t)j * n + i]);
+        Lf[e] = v + (i == j ? jitter : 0.0);
+        if (Kout) { Kout[mat * nn + e] = v; Kout[mat * nn + (size_t)j * n + i] = v; }
+      }
+    }
+    __syncthreads();
+    cta_chol_inverse(Lf, Linv, T, n, sm);
+    const int infoK = sm.info;
+    cta_gemm(n, n, n, 1.0, Linv, 1, n, Linv, n, 1, 0.0, ki, n, sm);
+    if (band >= 0) {
+      for (size_t e = tid; e < nn; e += kFT) {
+        const int i = (int)(e / n), j = (int)(e % n);
+        if (abs(i - j) > band) { ci[e] = 0.0; mo[e] = 0.0; ki[e] = 0.0; }
+      }
+    }
+    if (tid == 0) info[mat] = infoC ? infoC : -infoK;
+    __syncthreads();
+  }
+}
+
+int factor_grid(int nmat) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int g = 2 * sms;
+  return nmat < g ? nmat : g;
+}
+
+}  // namespace
+
+extern "C" size_t magi_b200_factor_workspace_bytes(int nmat, int n) {
+  if (nmat <= 0 || n <= 0) return 0;
+  // sized for the largest grid any device in the box would get (2 CTAs per SM, <= 148 SMs on B200);
+  // the launch clamps its grid to what this many bytes can serve.
+  const size_t per = (2 * (size_t)n * n + (size_t)kNB * n) * sizeof(double);
+  const int g = nmat < 296 ? nmat : 296;
+  return per * g;
+}
+
+extern "C" int magi_b200_factor_derive(const double* C, const double* Cp, const double* Cpp, int nmat, int n,
+                                       int band, double jitter, double* Cinv, double* m, double* Kinv, double* K,
+                                       int32_t* info, void* workspace, size_t workspace_bytes,
+                                       magi_stream_t stream) {
+  if (!C) return -1;
+  if (!Cp) return -2;
+  if (!Cpp) return -3;
+  if (nmat <= 0) return -4;
+  if (n <= 1) return -5;
+  if (!(jitter >= 0.0)) return -7;
+  if (!Cinv) return -8;
+  if (!m) return -9;
+  if (!Kinv) return -10;
+  if (!info) return -12;
+  const size_t per = (2 * (size_t)n * n + (size_t)kNB * n) * sizeof(double);
+  int grid = factor_grid(nmat);
+  if (!workspace || workspace_bytes < per) return -13;
+  if ((size_t)grid * per > workspace_bytes) grid = (int)(workspace_bytes / per);
+  cudaError_t e = cudaFuncSetAttribute(factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(FactorSmem));
+  if (e != cudaSuccess) return magi_cuda_status(e);
+  factor_kernel<<<grid, kFT, sizeof(FactorSmem), static_cast<cudaStream_t>(stream)>>>(
+      C, Cp, Cpp, nmat, n, band, jitter, Cinv, m, Kinv, K, info, static_cast<double*>(workspace));
+  return magi_cuda_status(cudaGetLastError());
+}

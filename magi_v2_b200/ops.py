@@ -1,0 +1,233 @@
+"""The C-ABI entry points exposed as PyTorch custom operators, ``torch.ops.magi_b200.*``.
+
+PyTorch is plumbing here (device memory, streams); each op validates its tensors, then passes raw
+device pointers and the current CUDA stream to libmagi_b200.so.  Ops exist for CUDA tensors only
+(no CPU kernels are registered: calling one with CPU tensors raises NotImplementedError)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import HmcConfig, Problem, check, lib
+
+Tensor = torch.Tensor
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(t: Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _chk(t: Tensor, name: str, dtype=torch.float64, shape=None):
+    if not t.is_cuda:
+        raise RuntimeError(f"magi_b200: {name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"magi_b200: {name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"magi_b200: {name} must be contiguous")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise RuntimeError(f"magi_b200: {name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+
+
+# ------------------------------------------------------------------------------------------------
+# (1) covariance build
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("magi_b200::cov_build", mutates_args=(), device_types="cuda")
+def cov_build(I: Tensor, phi1: Tensor, phi2: Tensor, nu: float, uniform_grid: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """I [n] (shared grid) or [B,n]; phi1, phi2 [B,D] -> C, Cp, Cpp each [B,D,n,n]."""
+    _chk(phi1, "phi1"); _chk(phi2, "phi2", shape=phi1.shape); _chk(I, "I")
+    B, D = phi1.shape
+    n = I.shape[-1]
+    stride = 0 if I.dim() == 1 else n
+    if I.dim() == 2 and I.shape[0] != B:
+        raise RuntimeError("magi_b200: I must be [n] or [B,n]")
+    with torch.cuda.device(phi1.device):
+        out = [torch.empty((B, D, n, n), dtype=torch.float64, device=phi1.device) for _ in range(3)]
+        st = lib().magi_b200_cov_build(_ptr(I), stride, _ptr(phi1), _ptr(phi2), float(nu), B, D, n,
+                                       _lib.COV_UNIFORM_GRID if uniform_grid else 0,
+                                       _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream(phi1))
+    check(st, "cov_build")
+    return out[0], out[1], out[2]
+
+
+@cov_build.register_fake
+def _(I, phi1, phi2, nu, uniform_grid):
+    B, D = phi1.shape
+    n = I.shape[-1]
+    return tuple(phi1.new_empty((B, D, n, n)) for _ in range(3))
+
+
+# ------------------------------------------------------------------------------------------------
+# (2) factorise + derive
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("magi_b200::factor_derive", mutates_args=(), device_types="cuda")
+def factor_derive(C_: Tensor, Cp: Tensor, Cpp: Tensor, band: int, jitter: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """C, Cp, Cpp [...,n,n] -> (Cinv, m, Kinv, K, info[...]) ; band < 0 = no banding."""
+    _chk(C_, "C"); _chk(Cp, "Cp", shape=C_.shape); _chk(Cpp, "Cpp", shape=C_.shape)
+    n = C_.shape[-1]
+    nmat = C_.numel() // (n * n)
+    with torch.cuda.device(C_.device):
+        Cinv, m, Kinv, K = (torch.empty_like(C_) for _ in range(4))
+        info = torch.empty(C_.shape[:-2], dtype=torch.int32, device=C_.device)
+        wsb = lib().magi_b200_factor_workspace_bytes(nmat, n)
+        ws = torch.empty(wsb // 8, dtype=torch.float64, device=C_.device)
+        st = lib().magi_b200_factor_derive(_ptr(C_), _ptr(Cp), _ptr(Cpp), nmat, n, int(band), float(jitter),
+                                           _ptr(Cinv), _ptr(m), _ptr(Kinv), _ptr(K), _ptr(info), _ptr(ws), wsb,
+                                           _stream(C_))
+    check(st, "factor_derive")
+    return Cinv, m, Kinv, K, info
+
+
+@factor_derive.register_fake
+def _(C_, Cp, Cpp, band, jitter):
+    return (torch.empty_like(C_), torch.empty_like(C_), torch.empty_like(C_), torch.empty_like(C_),
+            C_.new_empty(C_.shape[:-2], dtype=torch.int32))
+
+
+# ------------------------------------------------------------------------------------------------
+# (3a) pack
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("magi_b200::pack_matrices", mutates_args=(), device_types="cuda")
+def pack_matrices(Cinv: Tensor, m: Tensor, Kinv: Tensor) -> Tensor:
+    """Cinv, m, Kinv [B,D,n,n] -> opaque packed buffer (float64, 1-D)."""
+    _chk(Cinv, "Cinv"); _chk(m, "m", shape=Cinv.shape); _chk(Kinv, "Kinv", shape=Cinv.shape)
+    if Cinv.dim() != 4:
+        raise RuntimeError("magi_b200: matrices must be [B,D,n,n]")
+    B, D, n, _ = Cinv.shape
+    with torch.cuda.device(Cinv.device):
+        packed = torch.empty(lib().magi_b200_packed_bytes(B, D, n) // 8, dtype=torch.float64, device=Cinv.device)
+        st = lib().magi_b200_pack_matrices(_ptr(Cinv), _ptr(m), _ptr(Kinv), B, D, n, _ptr(packed), _stream(Cinv))
+    check(st, "pack_matrices")
+    return packed
+
+
+@pack_matrices.register_fake
+def _(Cinv, m, Kinv):
+    B, D, n, _ = Cinv.shape
+    npad = (n + 7) // 8 * 8
+    return Cinv.new_empty((B * D * 3 * npad * npad,))
+
+
+# ------------------------------------------------------------------------------------------------
+# problem constants
+# ------------------------------------------------------------------------------------------------
+class PosteriorProblem:
+    """Device-resident constants of the log-posterior for B datasets (what the reference's
+    ``unnormalized_log_prob`` closes over, magi_v2.py:294-300) + the ctypes view of them."""
+
+    def __init__(self, model: str, packed: Tensor, mu: Tensor, y: Tensor, mask: Tensor, N_ds: Tensor,
+                 beta: Tensor, LB: Tensor, n: int):
+        self.model = model
+        self.model_id = _lib.MODEL_IDS[model]
+        D_, P_ = C.c_int(), C.c_int()
+        lib().magi_b200_model_dims(self.model_id, C.byref(D_), C.byref(P_))
+        self.D, self.P = D_.value, P_.value
+        self.B, self.n = mu.shape[0], int(n)
+        _chk(mu, "mu", shape=(self.B, self.D)); _chk(y, "y", shape=(self.B, self.n, self.D))
+        _chk(mask, "mask", dtype=torch.uint8, shape=(self.B, self.n, self.D))
+        _chk(N_ds, "N_ds", shape=(self.B, self.D)); _chk(beta, "beta", shape=(self.B,))
+        _chk(LB, "LB", shape=(self.B, self.D)); _chk(packed, "packed")
+        if packed.numel() * 8 != lib().magi_b200_packed_bytes(self.B, self.D, self.n):
+            raise RuntimeError("magi_b200: packed buffer has the wrong size for (B, D, n)")
+        self.packed, self.mu, self.y, self.mask, self.N_ds, self.beta, self.LB = packed, mu, y, mask, N_ds, beta, LB
+        self.device = mu.device
+        self._ws = None
+
+    def struct(self, R: int) -> Problem:
+        return Problem(self.model_id, self.B, int(R), self.n, self.D, self.P, self.packed.data_ptr(),
+                       self.mu.data_ptr(), self.y.data_ptr(), self.mask.data_ptr(), self.N_ds.data_ptr(),
+                       self.beta.data_ptr(), self.LB.data_ptr())
+
+    def workspace(self, R: int) -> Tuple[Optional[Tensor], int]:
+        pb = self.struct(R)
+        nbytes = lib().magi_b200_sampler_workspace_bytes(C.byref(pb))
+        if self._ws is None or self._ws.numel() * 8 < nbytes:
+            self._ws = torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=self.device)
+        return self._ws, nbytes
+
+    # -- (3b) ------------------------------------------------------------------------------------
+    def logpost_grad(self, X: Tensor, sig_pre: Tensor, th_pre: Tensor, beta_temp: Tensor):
+        """X [B,R,n,D], sig_pre [B,R,D], th_pre [B,R,P], beta_temp [B,R] ->
+        (lp [B,R], gX, gsig, gth) -- value and gradient of magi_v2.py:308-348."""
+        R = X.shape[1]
+        _chk(X, "X", shape=(self.B, R, self.n, self.D)); _chk(sig_pre, "sig_pre", shape=(self.B, R, self.D))
+        _chk(th_pre, "th_pre", shape=(self.B, R, self.P)); _chk(beta_temp, "beta_temp", shape=(self.B, R))
+        with torch.cuda.device(self.device):
+            lp = torch.empty((self.B, R), dtype=torch.float64, device=self.device)
+            gX, gsig, gth = torch.empty_like(X), torch.empty_like(sig_pre), torch.empty_like(th_pre)
+            ws, nb = self.workspace(R)
+            pb = self.struct(R)
+            st = lib().magi_b200_logpost_grad(C.byref(pb), _ptr(X), _ptr(sig_pre), _ptr(th_pre), _ptr(beta_temp),
+                                              _ptr(lp), _ptr(gX), _ptr(gsig), _ptr(gth), _ptr(ws), nb, _stream(X))
+        check(st, "logpost_grad")
+        return lp, gX, gsig, gth
+
+    # -- (3c) ------------------------------------------------------------------------------------
+    def leapfrog_(self, X, sig_pre, th_pre, pX, psig, pth, eps, beta_temp, n_steps: int):
+        """In-place leapfrog trajectory with the given momenta; returns lp at the end point."""
+        R = X.shape[1]
+        for t, nm, shp in ((X, "X", (self.B, R, self.n, self.D)), (pX, "pX", (self.B, R, self.n, self.D)),
+                           (sig_pre, "sig_pre", (self.B, R, self.D)), (psig, "psig", (self.B, R, self.D)),
+                           (th_pre, "th_pre", (self.B, R, self.P)), (pth, "pth", (self.B, R, self.P)),
+                           (eps, "eps", (self.B, R)), (beta_temp, "beta_temp", (self.B, R))):
+            _chk(t, nm, shape=shp)
+        with torch.cuda.device(self.device):
+            lp = torch.empty((self.B, R), dtype=torch.float64, device=self.device)
+            ws, nb = self.workspace(R)
+            pb = self.struct(R)
+            st = lib().magi_b200_leapfrog(C.byref(pb), _ptr(X), _ptr(sig_pre), _ptr(th_pre), _ptr(pX), _ptr(psig),
+                                          _ptr(pth), _ptr(eps), _ptr(beta_temp), int(n_steps), _ptr(lp), _ptr(ws),
+                                          nb, _stream(X))
+        check(st, "leapfrog")
+        return lp
+
+    # -- (3d) ------------------------------------------------------------------------------------
+    def hmc_run_(self, X, sig_pre, th_pre, eps, da_state, *, n_iter: int, n_leapfrog: int, iter0: int = 0,
+                 num_adapt: int = 0, accum_from: int = 0, min_temp: float = 0.1, fixed_beta_temp: float = 0.0,
+                 target_accept: float = 0.75, seed: int = 0, chain_id0: int = 0, keep_theta=True,
+                 keep_sigma=True, keep_X=False, X_sum: Optional[Tensor] = None, X_sumsq: Optional[Tensor] = None):
+        """Run n_iter HMC transitions in place on (X, sig_pre, th_pre, eps, da_state); returns a dict of
+        traces (thetas_samps, sigma_sqs_samps, X_samps, accept_prob, lp)."""
+        R = X.shape[1]
+        _chk(X, "X", shape=(self.B, R, self.n, self.D)); _chk(sig_pre, "sig_pre", shape=(self.B, R, self.D))
+        _chk(th_pre, "th_pre", shape=(self.B, R, self.P)); _chk(eps, "eps", shape=(self.B, R))
+        _chk(da_state, "da_state", shape=(self.B, R, 4))
+        dev = self.device
+        with torch.cuda.device(dev):
+            mk = lambda *s: torch.empty(s, dtype=torch.float64, device=dev)
+            th_s = mk(n_iter, self.B, R, self.P) if keep_theta else None
+            sg_s = mk(n_iter, self.B, R, self.D) if keep_sigma else None
+            X_s = mk(n_iter, self.B, R, self.n, self.D) if keep_X else None
+            acc, lpt = mk(n_iter, self.B, R), mk(n_iter, self.B, R)
+            cfg = HmcConfig(int(n_iter), int(n_leapfrog), int(iter0), int(num_adapt), int(accum_from),
+                            float(min_temp), float(fixed_beta_temp), float(target_accept), int(seed),
+                            int(chain_id0))
+            ws, nb = self.workspace(R)
+            pb = self.struct(R)
+            st = lib().magi_b200_hmc_run(C.byref(pb), C.byref(cfg), _ptr(X), _ptr(sig_pre), _ptr(th_pre), _ptr(eps),
+                                         _ptr(da_state), _ptr(th_s), _ptr(sg_s), _ptr(X_s), _ptr(X_sum),
+                                         _ptr(X_sumsq), _ptr(acc), _ptr(lpt), _ptr(ws), nb, _stream(X))
+        check(st, "hmc_run")
+        return {"thetas_samps": th_s, "sigma_sqs_samps": sg_s, "X_samps": X_s, "accept_prob": acc, "lp": lpt}
+
+
+# ------------------------------------------------------------------------------------------------
+# (3b) as a registered operator (functional form; the class above is the stateful convenience)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("magi_b200::logpost_grad", mutates_args=(), device_types="cuda")
+def logpost_grad(model_id: int, X: Tensor, sig_pre: Tensor, th_pre: Tensor, beta_temp: Tensor, packed: Tensor,
+                 mu: Tensor, y: Tensor, mask: Tensor, N_ds: Tensor, beta: Tensor, LB: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    name = {v: k for k, v in _lib.MODEL_IDS.items()}[model_id]
+    prob = PosteriorProblem(name, packed, mu, y, mask, N_ds, beta, LB, X.shape[2])
+    return prob.logpost_grad(X, sig_pre, th_pre, beta_temp)
+
+
+@logpost_grad.register_fake
+def _(model_id, X, sig_pre, th_pre, beta_temp, packed, mu, y, mask, N_ds, beta, LB):
+    return X.new_empty(X.shape[:2]), torch.empty_like(X), torch.empty_like(sig_pre), torch.empty_like(th_pre)

@@ -1,0 +1,131 @@
+"""Generate the committed fixtures under tests/golden/ (run in the build container only:
+needs /root/reference).  TEST INFRASTRUCTURE -- see oracle/__init__.py.
+
+    python -m oracle.make_golden
+
+Fixtures:
+  build_kat.npz       GENUINE reference `_build_matrices` (magi_v2.py:774-823) outputs C, m, K for small
+                      grids, plus row/column probes and norms at n = 161 / 321; Matern blocks
+                      (Kappa, p_Kappa, Kappa_pp) from the restatement (bit-identical C pins it).
+  grid_kat.npz        GENUINE `_discretize` / `_linear_interpolate` outputs.
+  seir_datasets.npz   the 21 SEIR CSVs of the reference, thinned as vignette.ipynb:100-113 does
+                      (t <= 4, every 50th row): ts_obs [81], X_obs [21, 81, 4] (S,E,I,R _obs columns),
+                      X_true [21, 81, 4], names.  Data, not code.
+  logpost_kat.npz     seeded inputs and the restated log-posterior value + autograd gradient
+                      (oracle.magi_oracle) for every registry model at small n; matrices come from
+                      the genuine `_build_matrices` + tf_pinv stand-in + band.
+"""
+import glob
+import os
+
+import numpy as np
+import pandas as pd
+
+from . import magi_oracle as mo
+from .ref_loader import REFERENCE_DIR, reference_object
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def build_kat(ref):
+    out = {}
+    cases = [("appB", np.array([0, .025, .05, .075, .1]), 0.02, 0.23, 2.01),
+             ("n21", np.linspace(0, 1, 21), 0.0085, 0.375, 2.01),
+             ("n41", np.linspace(0, 4, 41), 0.034, 0.23, 2.01),
+             ("n33nu25", np.linspace(0, 2, 33), 0.024, 0.109, 2.5),
+             ("n17ragged", np.sort(np.random.default_rng(1).uniform(0, 2, 17)), 0.02, 0.3, 2.01)]
+    for name, I, p1, p2, v in cases:
+        C, m, K = ref._build_matrices(I.reshape(-1, 1), p1, p2, v)
+        Kap, pK, Kpp = mo.matern_blocks(I, p1, p2, v)
+        assert np.array_equal(Kap, C)
+        out[f"{name}_I"] = I; out[f"{name}_hp"] = np.array([p1, p2, v])
+        out[f"{name}_C"] = C; out[f"{name}_m"] = m; out[f"{name}_K"] = K
+        out[f"{name}_pK"] = pK; out[f"{name}_Kpp"] = Kpp
+    for n, p2 in ((161, 0.375), (161, 0.109), (321, 0.23)):
+        I = np.linspace(0, 4, n)
+        C, m, K = ref._build_matrices(I.reshape(-1, 1), 0.0085, p2, 2.01)
+        Kap, pK, Kpp = mo.matern_blocks(I, 0.0085, p2, 2.01)
+        tag = f"n{n}_phi2_{p2}"
+        out[f"{tag}_hp"] = np.array([0.0085, p2, 2.01])
+        for nm, A in (("C", C), ("m", m), ("K", K), ("pK", pK), ("Kpp", Kpp)):
+            out[f"{tag}_{nm}_row0"] = A[0]; out[f"{tag}_{nm}_rowmid"] = A[n // 2]
+            out[f"{tag}_{nm}_diag"] = np.diag(A); out[f"{tag}_{nm}_fro"] = np.linalg.norm(A)
+    np.savez_compressed(os.path.join(OUT, "build_kat.npz"), **out)
+
+
+def grid_kat(ref):
+    rng = np.random.default_rng(2)
+    ts = np.linspace(0, 4, 11)
+    X = rng.normal(size=(11, 3))
+    X[rng.uniform(size=X.shape) < 0.3] = np.nan
+    X[0] = 1.0; X[-1] = 2.0
+    out = {"ts": ts, "X": X}
+    for disc in (0, 1, 2):
+        I, Xd = ref._discretize(ts, X, disc)
+        out[f"I_d{disc}"] = I; out[f"Xd_d{disc}"] = Xd
+        out[f"Xi_d{disc}"] = ref._linear_interpolate(Xd)
+    np.savez_compressed(os.path.join(OUT, "grid_kat.npz"), **out)
+
+
+def seir_datasets():
+    files = [os.path.join(REFERENCE_DIR, "data", "SEIR_seed=0.csv")]
+    for a in ("0.05", "0.15"):
+        for s in range(10):
+            files.append(os.path.join(REFERENCE_DIR, "data", f"SEIR_beta=6_gamma=0.6_sigma=1.8_alpha={a}_seed={s}.csv"))
+    Xo, Xt, names, ts = [], [], [], None
+    for f in files:
+        raw = pd.read_csv(f).query("t <= 4.0")                                     # vignette.ipynb:104
+        obs = raw.iloc[::int((raw.index.shape[0] - 1) / (20 * 4.0))]               # :105
+        ts = obs.t.values.astype(np.float64)
+        Xo.append(obs[["S_obs", "E_obs", "I_obs", "R_obs"]].to_numpy().astype(np.float64))
+        Xt.append(obs[["S_true", "E_true", "I_true", "R_true"]].to_numpy().astype(np.float64))
+        names.append(os.path.basename(f))
+    np.savez_compressed(os.path.join(OUT, "seir_datasets.npz"), ts_obs=ts, X_obs=np.array(Xo), X_true=np.array(Xt),
+                        names=np.array(names))
+
+
+def logpost_kat(ref):
+    out = {}
+    rng = np.random.default_rng(3)
+    for name, model in mo.MODELS.items():
+        D, P = model.D, model.P
+        N = 9
+        ts = np.linspace(0, 2, N)
+        X_obs = np.abs(rng.normal(0.3, 0.2, size=(N, D)))
+        X_obs[rng.uniform(size=X_obs.shape) < 0.2] = np.nan
+        X_obs[0] = 0.2; X_obs[-1] = 0.4
+        phi1 = rng.uniform(0.005, 0.05, D); phi2 = rng.uniform(0.2, 0.6, D)
+        I, _ = mo.discretize(ts, X_obs, 1)
+        n = I.shape[0]
+        band = 6
+        mats = [np.zeros((D, n, n)) for _ in range(3)]
+        for d in range(D):
+            C_d, m_d, K_d = ref._build_matrices(I, phi1[d], phi2[d], 2.01)       # genuine reference
+            mats[0][d], mats[1][d], mats[2][d] = mo.tf_pinv(C_d), m_d, mo.tf_pinv(K_d)
+        mats = [mo.band_part(A, band) for A in mats]
+        c = mo.make_constants(ts, X_obs, 1, phi1, phi2, band, model.f_vec, matrices=mats)
+        X = mo.linear_interpolate(mo.discretize(ts, X_obs, 1)[1]) + 0.02 * rng.standard_normal((n, D))
+        s = rng.normal(-4, 1, D); tau = rng.normal(0.5, 1.0, P); bt = 0.37
+        lp, gX, gs, gt = mo.log_posterior_and_grad_autograd(X, s, tau, bt, c)
+        lp_np = mo.log_posterior(X, s, tau, bt, c)
+        assert abs(lp - lp_np) <= 1e-12 * abs(lp)
+        for k, v in dict(ts=ts, X_obs=X_obs, phi1=phi1, phi2=phi2, band=np.array(band), Cinv=mats[0], m=mats[1],
+                         Kinv=mats[2], X=X, s=s, tau=tau, bt=np.array(bt), lp=np.array(lp), gX=gX, gs=gs,
+                         gt=gt).items():
+            out[f"{name}_{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "logpost_kat.npz"), **out)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = reference_object()
+    build_kat(ref)
+    grid_kat(ref)
+    seir_datasets()
+    logpost_kat(ref)
+    for f in sorted(glob.glob(os.path.join(OUT, "*.npz"))):
+        print(f, os.path.getsize(f))
+
+
+if __name__ == "__main__":
+    main()

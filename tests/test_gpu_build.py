@@ -1,0 +1,136 @@
+"""Parity of the CUDA covariance build and Cholesky-based factorisation with the reference's
+`_build_matrices` (magi_v2.py:774-823) and the SVD pseudo-inverses at :126-128.
+
+Tolerances (hard part 1): the Matern blocks C, C', C'' are compared entry-wise
+(1e-12 of the block's scale); m, K, C^-1, K^-1 inherit a forward error ~ eps * cond(C) from the
+reference's own pinv route, so they are compared with tolerance c * eps * cond(C)."""
+import numpy as np
+import pytest
+
+from oracle import magi_oracle as mo
+from tests.helpers import load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(np.float64).eps
+
+
+def _T(a, device):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=device)
+
+
+def _cov(I, phi1, phi2, nu, device, uniform=False):
+    import torch
+    from magi_v2_b200 import ops
+    C, Cp, Cpp = ops.cov_build(_T(I, device), _T(phi1, device), _T(phi2, device), nu, uniform)
+    torch.cuda.synchronize()
+    return C.cpu().numpy(), Cp.cpu().numpy(), Cpp.cpu().numpy()
+
+
+@pytest.mark.parametrize("tag", ["appB", "n21", "n41", "n33nu25", "n17ragged"])
+def test_matern_blocks_match_reference_golden(tag, cuda_device):
+    g = load_golden("build_kat.npz")
+    I = g[f"{tag}_I"]
+    p1, p2, v = g[f"{tag}_hp"]
+    C, Cp, Cpp = _cov(I, [[p1]], [[p2]], float(v), cuda_device)
+    assert relerr(C[0, 0], g[f"{tag}_C"]) <= 1e-12          # genuine reference output
+    assert relerr(Cp[0, 0], g[f"{tag}_pK"]) <= 1e-12
+    assert relerr(Cpp[0, 0], g[f"{tag}_Kpp"]) <= 1e-12
+    assert np.array_equal(Cp[0, 0], -Cp[0, 0].T) and np.array_equal(C[0, 0], C[0, 0].T)
+
+
+@pytest.mark.parametrize("n,phi2", [(161, 0.375), (161, 0.109), (321, 0.23)])
+def test_matern_blocks_full_size_probes(n, phi2, cuda_device):
+    g = load_golden("build_kat.npz")
+    tag = f"n{n}_phi2_{phi2}"
+    I = np.linspace(0, 4, n)
+    for uniform in (False, True):
+        C, Cp, Cpp = _cov(I, [[0.0085]], [[phi2]], 2.01, cuda_device, uniform)
+        for A, nm in ((C, "C"), (Cp, "pK"), (Cpp, "Kpp")):
+            A = A[0, 0]
+            scale = np.abs(g[f"{tag}_{nm}_row0"]).max()
+            assert np.abs(A[0] - g[f"{tag}_{nm}_row0"]).max() <= 1e-12 * scale
+            assert np.abs(A[n // 2] - g[f"{tag}_{nm}_rowmid"]).max() <= 1e-12 * scale
+            assert np.abs(np.diag(A) - g[f"{tag}_{nm}_diag"]).max() <= 1e-12 * scale
+            assert abs(np.linalg.norm(A) - g[f"{tag}_{nm}_fro"]) <= 1e-12 * g[f"{tag}_{nm}_fro"]
+
+
+def test_batched_build_many_datasets(cuda_device):
+    rng = np.random.default_rng(0)
+    B, D, n = 5, 3, 37
+    I = np.sort(rng.uniform(0, 3, (B, n)), axis=1)
+    phi1 = rng.uniform(0.005, 0.05, (B, D)); phi2 = rng.uniform(0.1, 0.5, (B, D))
+    C, Cp, Cpp = _cov(I, phi1, phi2, 2.01, cuda_device)
+    for b in range(B):
+        for d in range(D):
+            Kap, pK, Kpp = mo.matern_blocks(I[b], phi1[b, d], phi2[b, d], 2.01)
+            assert relerr(C[b, d], Kap) <= 1e-12 and relerr(Cp[b, d], pK) <= 1e-12 and relerr(Cpp[b, d], Kpp) <= 1e-12
+
+
+@pytest.mark.parametrize("n,phi2,band", [(21, 0.375, None), (41, 0.23, 10), (161, 0.109, 80), (161, 0.375, 80),
+                                          (130, 0.3, None)])
+def test_factor_derive_matches_reference_route(n, phi2, band, cuda_device):
+    import torch
+    from magi_v2_b200 import ops
+    I = np.linspace(0, 4.0 * (n - 1) / 160.0 if n != 21 else 1.0, n)
+    phi1 = 0.0085
+    C_ref, m_ref, K_ref = mo.build_matrices(I, phi1, phi2, 2.01)          # reference route (pinv)
+    Cinv_ref, Kinv_ref = mo.tf_pinv(C_ref), mo.tf_pinv(K_ref)
+    cond = np.linalg.cond(C_ref)
+    Kap, pK, Kpp = mo.matern_blocks(I, phi1, phi2, 2.01)
+    Cinv, m, Kinv, K, info = ops.factor_derive(_T(Kap[None], cuda_device), _T(pK[None], cuda_device),
+                                               _T(Kpp[None], cuda_device), -1 if band is None else band, 0.0)
+    torch.cuda.synchronize()
+    assert int(info[0]) == 0
+    Cinv, m, Kinv, K = (a.cpu().numpy()[0] for a in (Cinv, m, Kinv, K))
+    tol = 50 * EPS * cond
+    assert relerr(K, K_ref) <= tol
+    assert relerr(m, mo.band_part(m_ref, band)) <= tol
+    assert relerr(Cinv, mo.band_part(Cinv_ref, band)) <= tol
+    assert relerr(Kinv, mo.band_part(Kinv_ref, band)) <= tol * np.linalg.cond(K_ref)
+    if band is None:
+        # independent of the reference route: residuals of the inverses
+        assert np.abs(Cinv @ C_ref - np.eye(n)).max() <= 50 * EPS * cond
+        assert np.abs(Kinv @ K - np.eye(n)).max() <= 1e-10
+
+
+def test_factor_reports_non_positive_definite(cuda_device):
+    import torch
+    from magi_v2_b200 import ops
+    n = 9
+    A = np.eye(n); A[4, 4] = -1.0
+    Z = np.zeros((1, n, n))
+    *_, info = ops.factor_derive(_T(A[None], cuda_device), _T(Z, cuda_device), _T(np.eye(n)[None], cuda_device), -1, 0.0)
+    torch.cuda.synchronize()
+    assert int(info[0]) == 5
+
+
+def test_end_to_end_build_feeds_the_log_posterior(cuda_device):
+    """cov_build -> factor_derive -> pack -> logpost_grad entirely on the device, checked against the
+    oracle evaluated on the DEVICE-built matrices (isolates the evaluation from the pinv-vs-Cholesky
+    conditioning difference)."""
+    import torch
+    from magi_v2_b200 import ops
+    from tests.helpers import random_state, synth_constants
+    model = "seir4"
+    c0 = synth_constants(model, seed=77, N=21, band=12)
+    rng = np.random.default_rng(4)
+    D = 4
+    phi1 = rng.uniform(0.005, 0.05, (1, D)); phi2 = rng.uniform(0.2, 0.6, (1, D))
+    C, Cp, Cpp = ops.cov_build(_T(c0.I.ravel(), cuda_device), _T(phi1, cuda_device), _T(phi2, cuda_device), 2.01, True)
+    Cinv, m, Kinv, K, info = ops.factor_derive(C, Cp, Cpp, 12, 0.0)
+    assert int(info.abs().max()) == 0
+    c = mo.PosteriorConstants(I=c0.I, mu_ds=c0.mu_ds, C_d_invs=Cinv[0].cpu().numpy(), m_ds=m[0].cpu().numpy(),
+                              K_d_invs=Kinv[0].cpu().numpy(), N_ds=c0.N_ds, not_nan_idxs=c0.not_nan_idxs,
+                              not_nan_cols=c0.not_nan_cols, y_tau_ds_observed=c0.y_tau_ds_observed, beta=c0.beta,
+                              sigma_sqs_LB=c0.sigma_sqs_LB, f_vec=c0.f_vec)
+    from tests.helpers import device_problem
+    prob = device_problem([c], model, cuda_device)
+    X, s, tau = random_state(c, model, rng, 4)
+    lp, gX, gs, gt = prob.logpost_grad(_T(X[None], cuda_device), _T(s[None], cuda_device), _T(tau[None], cuda_device),
+                                       _T(np.full((1, 4), 0.8), cuda_device))
+    torch.cuda.synchronize()
+    for r in range(4):
+        o = mo.log_posterior_and_grad_autograd(X[r], s[r], tau[r], 0.8, c)
+        assert abs(float(lp[0, r]) - o[0]) <= 1e-9 * abs(o[0])
+        assert relerr(gX[0, r].cpu().numpy(), o[1]) <= 1e-9
