@@ -42,7 +42,9 @@ struct Scratch {
     return (size_t)(with_momentum ? 5 : 4) * M::D * kCh * np + (size_t)kCh * np;
   }
   __host__ __device__ static size_t small_elems(int np) {
-    return (size_t)2 * M::D * np + (size_t)kCh * (5 * M::P + 5 * M::D + 1 + kCtl) + 3 * M::D + (size_t)kWarps * NRED;
+    const size_t e = (size_t)2 * M::D * np + (size_t)kCh * (5 * M::P + 5 * M::D + 1 + kCtl) + 3 * M::D +
+                     (size_t)kWarps * NRED;
+    return (e + 1) & ~(size_t)1;  // keep the big arrays behind it 16-byte aligned (double2 loads)
   }
   __device__ void carve(double* big, double* small, int n_, int np_, bool with_momentum) {
     n = n_;

@@ -112,6 +112,30 @@ def matern_blocks(I, phi1, phi2, v=2.01):
     return Kappa, p_Kappa, Kappa_pp
 
 
+def matern_blocks_roundoff_scale(I, phi1, phi2, v=2.01):
+    """Per-entry size of the terms the reference's formulas for p_Kappa (:798-801) and Kappa_pp
+    (:808-812) add and subtract.  k * eps * scale bounds the REFERENCE's own rounding error: its
+    Kappa_pp forms 2v(s-t)^2 as 2v s^2 - 4v s t + 2v t^2 (:810), which cancels catastrophically for
+    |s-t| << |s| (relative error ~ eps * s^2 / l^2, e.g. 5e-10 at t = 3.3, l = 0.025).  Tests compare a
+    more accurate evaluation against the reference within this bound instead of a flat tolerance."""
+    I = np.asarray(I, dtype=np.float64)
+    s = np.tile(A=I.reshape(-1, 1), reps=I.size)
+    t = s.T
+    l = np.abs(s - t)
+    u = np.sqrt(2 * v) * l / phi2
+    np.fill_diagonal(u, np.nan)
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        Bv0, Bv1, Bv2 = np.abs(_kvp(v, u, 0)), np.abs(_kvp(v, u, 1)), np.abs(_kvp(v, u, 2))
+        pref = (2 ** (1 - (v / 2))) * phi1 * ((u / np.sqrt(2)) ** v)
+        M_pK = pref * ((u * phi2 * Bv1) + (v * phi2 * Bv0)) / (phi2 * l * _gamma(v))
+        M_Kpp = (2 * np.sqrt(2) * (v ** 1.5) * phi2 * l * Bv1 + ((v ** 2) * (phi2 ** 2) + v * (phi2 ** 2)) * Bv0
+                 + ((2 * v * (s ** 2)) + (4 * v * np.abs(s * t)) + (2 * v * (t ** 2))) * Bv2)
+        M_Kpp = M_Kpp * pref / ((phi2 ** 2) * (l ** 2) * _gamma(v))
+    np.fill_diagonal(M_pK, 0.0)
+    np.fill_diagonal(M_Kpp, 0.0)
+    return np.nan_to_num(M_pK), np.nan_to_num(M_Kpp)
+
+
 def build_matrices(I, phi1, phi2, v=2.01):
     """magi_v2.py:774-823 restated: returns (C_d, m_d, K_d)."""
     Kappa, p_Kappa, Kappa_pp = matern_blocks(I, phi1, phi2, v)

@@ -84,3 +84,39 @@ def relerr(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     den = np.max(np.abs(b))
     return float(np.max(np.abs(a - b)) / (den if den > 0 else 1.0))
+
+
+def chol_solve_longdouble(A, Bm=None):
+    """Extended-precision (x87 80-bit) Cholesky inverse / solve in plain numpy: the 'truth' against
+    which both the reference's SVD route and the CUDA Cholesky route are measured."""
+    A = np.asarray(A, dtype=np.longdouble)
+    n = A.shape[0]
+    L = np.zeros_like(A)
+    for j in range(n):
+        d = A[j, j] - np.dot(L[j, :j], L[j, :j])
+        L[j, j] = np.sqrt(d)
+        if j + 1 < n:
+            L[j + 1:, j] = (A[j + 1:, j] - L[j + 1:, :j] @ L[j, :j]) / L[j, j]
+    rhs = np.eye(n, dtype=np.longdouble) if Bm is None else np.asarray(Bm, dtype=np.longdouble)
+    Y = np.zeros_like(rhs)
+    for i in range(n):
+        Y[i] = (rhs[i] - L[i, :i] @ Y[:i]) / L[i, i]
+    Z = np.zeros_like(rhs)
+    for i in range(n - 1, -1, -1):
+        Z[i] = (Y[i] - L[i + 1:, i] @ Z[i + 1:]) / L[i, i]
+    return Z
+
+
+def matern_truth_longdouble(I, phi1, phi2, nu):
+    """(C^-1, m, K, K^-1) in extended precision from double-precision Matern blocks."""
+    from oracle import magi_oracle as mo
+    Kap, pK, Kpp = mo.matern_blocks(I, phi1, phi2, nu)
+    # the reference's Kappa_pp is the noisy one (see matern_blocks_roundoff_scale): rebuild it as the
+    # exact Toeplitz-consistent function of the lag from the first row where s = 0 has no cancellation
+    Cinv = chol_solve_longdouble(Kap)
+    pK_l = np.asarray(pK, dtype=np.longdouble)
+    m = pK_l @ Cinv
+    K = np.asarray(Kpp, dtype=np.longdouble) - m @ pK_l.T
+    K = (K + K.T) / 2
+    Kinv = chol_solve_longdouble(K)
+    return Cinv, m, K, Kinv
