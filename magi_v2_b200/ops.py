@@ -137,36 +137,108 @@ class PosteriorProblem:
             raise RuntimeError("magi_b200: packed buffer has the wrong size for (B, D, n)")
         self.packed, self.mu, self.y, self.mask, self.N_ds, self.beta, self.LB = packed, mu, y, mask, N_ds, beta, LB
         self.device = mu.device
-        self._ws = None
+        self._ws = {}
+        self._host = None
 
-    def struct(self, R: int) -> Problem:
-        return Problem(self.model_id, self.B, int(R), self.n, self.D, self.P, self.packed.data_ptr(),
-                       self.mu.data_ptr(), self.y.data_ptr(), self.mask.data_ptr(), self.N_ds.data_ptr(),
-                       self.beta.data_ptr(), self.LB.data_ptr())
+    def struct(self, R: int, b0: int = 0, b1: Optional[int] = None) -> Problem:
+        """magi_problem_t for datasets [b0, b1) (a view: pointers offset into the same buffers)."""
+        b1 = self.B if b1 is None else b1
+        npad = (self.n + 7) // 8 * 8
+        D, n = self.D, self.n
+        return Problem(self.model_id, b1 - b0, int(R), n, D, self.P,
+                       self.packed.data_ptr() + b0 * D * 3 * npad * npad * 8,
+                       self.mu.data_ptr() + b0 * D * 8, self.y.data_ptr() + b0 * n * D * 8,
+                       self.mask.data_ptr() + b0 * n * D, self.N_ds.data_ptr() + b0 * D * 8,
+                       self.beta.data_ptr() + b0 * 8, self.LB.data_ptr() + b0 * D * 8)
 
-    def workspace(self, R: int) -> Tuple[Optional[Tensor], int]:
-        pb = self.struct(R)
+    def workspace(self, R: int, slot: int = 0, n_datasets: Optional[int] = None) -> Tuple[Optional[Tensor], int]:
+        """Caller-owned scratch of the sampler kernels; one buffer per concurrent stream (`slot`)."""
+        pb = self.struct(R, 0, n_datasets)
         nbytes = lib().magi_b200_sampler_workspace_bytes(C.byref(pb))
-        if self._ws is None or self._ws.numel() * 8 < nbytes:
-            self._ws = torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=self.device)
-        return self._ws, nbytes
+        ws = self._ws.get(slot)
+        if ws is None or ws.numel() * 8 < nbytes:
+            ws = torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=self.device)
+            self._ws[slot] = ws
+        return ws, nbytes
 
     # -- (3b) ------------------------------------------------------------------------------------
-    def logpost_grad(self, X: Tensor, sig_pre: Tensor, th_pre: Tensor, beta_temp: Tensor):
+    def logpost_grad_out(self, R: int):
+        """Preallocated device outputs (lp [B,R], gX [B,R,n,D], gsig [B,R,D], gth [B,R,P])."""
+        mk = lambda *sh: torch.empty(sh, dtype=torch.float64, device=self.device)
+        return mk(self.B, R), mk(self.B, R, self.n, self.D), mk(self.B, R, self.D), mk(self.B, R, self.P)
+
+    def logpost_grad(self, X: Tensor, sig_pre: Tensor, th_pre: Tensor, beta_temp: Tensor, out=None):
         """X [B,R,n,D], sig_pre [B,R,D], th_pre [B,R,P], beta_temp [B,R] ->
         (lp [B,R], gX, gsig, gth) -- value and gradient of magi_v2.py:308-348."""
         R = X.shape[1]
         _chk(X, "X", shape=(self.B, R, self.n, self.D)); _chk(sig_pre, "sig_pre", shape=(self.B, R, self.D))
         _chk(th_pre, "th_pre", shape=(self.B, R, self.P)); _chk(beta_temp, "beta_temp", shape=(self.B, R))
         with torch.cuda.device(self.device):
-            lp = torch.empty((self.B, R), dtype=torch.float64, device=self.device)
-            gX, gsig, gth = torch.empty_like(X), torch.empty_like(sig_pre), torch.empty_like(th_pre)
+            lp, gX, gsig, gth = self.logpost_grad_out(R) if out is None else out
+            if out is not None:
+                _chk(lp, "lp", shape=(self.B, R)); _chk(gX, "gX", shape=X.shape)
+                _chk(gsig, "gsig", shape=sig_pre.shape); _chk(gth, "gth", shape=th_pre.shape)
             ws, nb = self.workspace(R)
             pb = self.struct(R)
             st = lib().magi_b200_logpost_grad(C.byref(pb), _ptr(X), _ptr(sig_pre), _ptr(th_pre), _ptr(beta_temp),
                                               _ptr(lp), _ptr(gX), _ptr(gsig), _ptr(gth), _ptr(ws), nb, _stream(X))
         check(st, "logpost_grad")
         return lp, gX, gsig, gth
+
+    # -- (3b) with HOST buffers: what a host-side sampler (the reference's TFP loop) would call ----------
+    def logpost_grad_host_out(self, R: int):
+        """Pinned host outputs for `logpost_grad_host`."""
+        mk = lambda *sh: torch.empty(sh, dtype=torch.float64).pin_memory()
+        return mk(self.B, R), mk(self.B, R, self.n, self.D), mk(self.B, R, self.D), mk(self.B, R, self.P)
+
+    def logpost_grad_host(self, X: Tensor, sig_pre: Tensor, th_pre: Tensor, beta_temp: Tensor, out=None,
+                          n_chunks: int = 8, n_streams: int = 3):
+        """Same as `logpost_grad` for HOST tensors (pinned for full speed): the batch is cut into
+        dataset chunks whose host->device copy, kernel launch and device->host copy are pipelined over
+        `n_streams` CUDA streams, so that PCIe in both directions overlaps the kernels.  Returns host
+        tensors (lp, gX, gsig, gth); the caller's current stream is ordered after all of it."""
+        R = X.shape[1]
+        for t, nm, shp in ((X, "X", (self.B, R, self.n, self.D)), (sig_pre, "sig_pre", (self.B, R, self.D)),
+                           (th_pre, "th_pre", (self.B, R, self.P)), (beta_temp, "beta_temp", (self.B, R))):
+            if t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous() or tuple(t.shape) != shp:
+                raise RuntimeError(f"magi_b200: {nm} must be a contiguous float64 host tensor of shape {shp}")
+        hout = self.logpost_grad_host_out(R) if out is None else out
+        with torch.cuda.device(self.device):
+            if self._host is None or self._host["R"] != R:
+                self._host = {"R": R, "in": tuple(torch.empty(t.shape, dtype=torch.float64, device=self.device)
+                                                   for t in (X, sig_pre, th_pre, beta_temp)),
+                              "out": self.logpost_grad_out(R),
+                              "streams": [torch.cuda.Stream(self.device) for _ in range(n_streams)]}
+            H = self._host
+            cur = torch.cuda.current_stream(self.device)
+            start = torch.cuda.Event()
+            start.record(cur)
+            n_chunks = max(1, min(n_chunks, self.B))
+            bounds = [self.B * c // n_chunks for c in range(n_chunks + 1)]
+            for c in range(n_chunks):
+                b0, b1 = bounds[c], bounds[c + 1]
+                if b1 == b0:
+                    continue
+                stq = H["streams"][c % len(H["streams"])]
+                stq.wait_event(start)
+                with torch.cuda.stream(stq):
+                    for d_t, h_t in zip(H["in"], (X, sig_pre, th_pre, beta_temp)):
+                        d_t[b0:b1].copy_(h_t[b0:b1], non_blocking=True)
+                    ws, nb = self.workspace(R, slot=1 + c % len(H["streams"]), n_datasets=bounds[1] + 1)
+                    pb = self.struct(R, b0, b1)
+                    dX, ds, dt, dbt = (t[b0:b1] for t in H["in"])
+                    lp, gX, gs, gt = (t[b0:b1] for t in H["out"])
+                    st = lib().magi_b200_logpost_grad(C.byref(pb), _ptr(dX), _ptr(ds), _ptr(dt), _ptr(dbt), _ptr(lp),
+                                                      _ptr(gX), _ptr(gs), _ptr(gt), _ptr(ws), nb,
+                                                      C.c_void_p(stq.cuda_stream))
+                    check(st, "logpost_grad")
+                    for h_t, d_t in zip(hout, H["out"]):
+                        h_t[b0:b1].copy_(d_t[b0:b1], non_blocking=True)
+            for stq in H["streams"]:
+                ev = torch.cuda.Event()
+                ev.record(stq)
+                cur.wait_event(ev)
+        return hout
 
     # -- (3c) ------------------------------------------------------------------------------------
     def leapfrog_(self, X, sig_pre, th_pre, pX, psig, pth, eps, beta_temp, n_steps: int):
