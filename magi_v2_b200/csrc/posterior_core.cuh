@@ -1,8 +1,12 @@
 // Device core of the MAGI log-posterior + analytic gradient (replaces magi_v2.py:308-348 and the
 // TF reverse-mode gradient TFP's leapfrog takes of it).  One CTA owns one dataset and a group of
-// up to 8 of its chains; the dataset's packed matrices sym(C^-1) | m | sym(K^-1) are streamed from
-// HBM/L2 once per evaluation and shared by the 8 chains.  Shared by the logpost_grad, leapfrog and
-// HMC kernels.
+// up to 8 of its chains.  The dataset's packed matrices sym(C^-1) | m | sym(K^-1) are streamed from
+// HBM/L2 once per evaluation and shared by the 8 chains: with 8 chains per matrix the four batched
+// mat-vecs per component become the dense contractions  [n x n] . [n x 8], which run on the FP64
+// tensor cores (mma.sync.m8n8k4.f64 -> DMMA) with N = 8 = chains.  Matrix fragments go straight
+// from global memory to registers (software-pipelined 128-bit loads, prefetched across phase
+// boundaries); the chain vectors are the B operand and live in shared memory.
+// Shared by the logpost_grad, leapfrog and HMC kernels.
 //
 // Math, per chain, "base" quantities WITHOUT the temperature factor beta_temp
 // (lp = beta_temp * L, grad lp = beta_temp * grad L):
@@ -14,18 +18,23 @@
 #include "common.cuh"
 #include "ode_models.cuh"
 
-constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
-constexpr int kCh = MAGI_CHAINS_PER_CTA;  // 8
+constexpr int kMaxWarps = 21;               // 672 threads: 96 registers per thread, one CTA per SM
+constexpr int kMaxThreads = kMaxWarps * 32;
+constexpr int kMinWarps = 8;                // pointwise phases map warp w to chain w % 8
+constexpr int kCh = MAGI_CHAINS_PER_CTA;    // 8
+constexpr int kU = 7;                       // 8-column steps per register batch (7 x 16 B per lane in flight)
 
-// Scratch arrays of one CTA.  Vector arrays are [D][8][np] (chain-major, grid index fastest) so
-// that lanes walking the grid index hit consecutive shared-memory banks.
+// chain stride of the shared-memory vector arrays: np + 2 doubles, so that the 128-bit B-fragment
+// loads of a quarter warp (2 chains x 4 column pairs) fall into 32 distinct banks
+__host__ __device__ static inline int magi_chain_stride(int np) { return np + 2; }
+
+// Scratch arrays of one CTA.  Vector arrays are [D][8][ns] (chain-major, grid index fastest).
 template <class M>
 struct Scratch {
-  int n, np;
-  double *Xc, *FR, *G, *GX;  // [D][8][np]   centred state, f -> residual r, g = 2 q, gradient
-  double* PX;                // [D][8][np]   momentum (HMC kernels only; else nullptr)
-  double* W;                 // [8][np]      m_d xc_d
+  int n, np, ns;
+  double *Xc, *FG, *GX;      // [D][8][ns]   centred state | f -> residual r -> g = 2 S_K r | gradient
+  double* PX;                // [D][8][ns]   momentum (HMC kernels only; else nullptr)
+  double* W;                 // [8][ns]      m_d xc_d, then g_d
   double *Y, *MK;            // [D][np]      observations / mask as 0.0 or 1.0
   double *tau, *th, *sgt;    // [P][8]       theta_pre, softplus, sigmoid
   double *s, *sig2, *sgs;    // [D][8]       sigma_pre, softplus + LB, sigmoid
@@ -33,24 +42,25 @@ struct Scratch {
   double *gtau, *gs;         // [P][8], [D][8] base gradient w.r.t. tau, s
   double* L;                 // [8]          base log-posterior
   double *mu, *Nd, *LB;      // [D]
-  double* wpart;             // [kWarps][NRED]
+  double* wpart;             // [kMaxWarps][NRED]
   double* ctl;               // [kCtl][8]    sampler control values (step size, energies, saved small state)
   static constexpr int kCtl = 16 + 2 * M::P + 2 * M::D;
   static constexpr int NRED = 2 + M::D + M::P;
 
   __host__ __device__ static size_t big_elems(int np, bool with_momentum) {
-    return (size_t)(with_momentum ? 5 : 4) * M::D * kCh * np + (size_t)kCh * np;
+    return (size_t)(with_momentum ? 4 : 3) * M::D * kCh * magi_chain_stride(np) + (size_t)kCh * magi_chain_stride(np);
   }
   __host__ __device__ static size_t small_elems(int np) {
     const size_t e = (size_t)2 * M::D * np + (size_t)kCh * (5 * M::P + 5 * M::D + 1 + kCtl) + 3 * M::D +
-                     (size_t)kWarps * NRED;
-    return (e + 1) & ~(size_t)1;  // keep the big arrays behind it 16-byte aligned (double2 loads)
+                     (size_t)kMaxWarps * NRED;
+    return (e + 1) & ~(size_t)1;  // keep the big arrays behind it 16-byte aligned (128-bit loads)
   }
   __device__ void carve(double* big, double* small, int n_, int np_, bool with_momentum) {
     n = n_;
     np = np_;
-    const size_t v = (size_t)M::D * kCh * np;
-    Xc = big; FR = Xc + v; G = FR + v; GX = G + v;
+    ns = magi_chain_stride(np_);
+    const size_t v = (size_t)M::D * kCh * ns;
+    Xc = big; FG = Xc + v; GX = FG + v;
     double* p = GX + v;
     PX = nullptr;
     if (with_momentum) { PX = p; p += v; }
@@ -64,139 +74,97 @@ struct Scratch {
     ps = p; p += M::D * kCh; gs = p; p += M::D * kCh;
     L = p; p += kCh;
     mu = p; p += M::D; Nd = p; p += M::D; LB = p; p += M::D;
-    wpart = p; p += kWarps * NRED;
+    wpart = p; p += kMaxWarps * NRED;
     ctl = p;
   }
-  __device__ __forceinline__ size_t vix(int d, int r, int j) const { return ((size_t)d * kCh + r) * np + j; }
+  __device__ __forceinline__ size_t vix(int d, int r, int j) const { return ((size_t)d * kCh + r) * ns + j; }
+  __device__ __forceinline__ size_t vsize() const { return (size_t)M::D * kCh * ns; }
 };
 
-// ---- reduce 16 per-lane values across the warp: butterfly that halves the value count per round.
-// On return lane L holds in v[0] the full sum of value index
-//   ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1).
-__device__ __forceinline__ void warp_reduce16(double (&v)[16], int lane) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const bool up = lane & 16;
-    const double send = up ? v[k] : v[k + 8];
-    const double keep = up ? v[k + 8] : v[k];
-    v[k] = keep + magi_shfl_xor(send, 16);
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const bool up = lane & 8;
-    const double send = up ? v[k] : v[k + 4];
-    const double keep = up ? v[k + 4] : v[k];
-    v[k] = keep + magi_shfl_xor(send, 8);
-  }
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const bool up = lane & 4;
-    const double send = up ? v[k] : v[k + 2];
-    const double keep = up ? v[k + 2] : v[k];
-    v[k] = keep + magi_shfl_xor(send, 4);
-  }
-  {
-    const bool up = lane & 2;
-    const double send = up ? v[0] : v[1];
-    const double keep = up ? v[1] : v[0];
-    v[0] = keep + magi_shfl_xor(send, 2);
-  }
-  v[0] += magi_shfl_xor(v[0], 1);
+// Pointwise phases: warp w serves chain w % 8; the warps of a chain interleave over the grid index.
+struct ChainMap {
+  int r, j0, jstride, nwr;
+};
+__device__ __forceinline__ ChainMap chain_map() {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  ChainMap cm;
+  cm.r = w & 7;
+  cm.nwr = (nw - cm.r + 7) >> 3;  // warps serving chain r (blockDim >= 8 warps)
+  cm.j0 = (w >> 3) * 32 + lane;
+  cm.jstride = 32 * cm.nwr;
+  return cm;
 }
 
-// y1[r][i] = scale1 * sum_j A1[i][j] x[r][j],  y2[r][i] = scale2 * sum_j A2[i][j] x[r][j]   (i < n)
-// Warp per row; lanes stride the row with 16-byte loads (coalesced 512 B per warp instruction).
-// A2 == nullptr: single matrix.
-__device__ __forceinline__ void matvec_rows(const double* __restrict__ A1, const double* __restrict__ A2,
-                                            const double* x, double* y1, double* y2, double scale1,
-                                            double scale2, int n, int np) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int npair = np >> 1;
-  for (int i = warp; i < n; i += kWarps) {
-    double acc[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) acc[k] = 0.0;
-    const double2* r1 = reinterpret_cast<const double2*>(A1 + (size_t)i * np);
-    const double2* r2 = A2 ? reinterpret_cast<const double2*>(A2 + (size_t)i * np) : nullptr;
-    for (int jp = lane; jp < npair; jp += 32) {
-      const double2 a1 = __ldg(r1 + jp);
-      double2 a2 = make_double2(0.0, 0.0);
-      if (r2) a2 = __ldg(r2 + jp);
-#pragma unroll
-      for (int r = 0; r < kCh; ++r) {
-        const double2 xv = *reinterpret_cast<const double2*>(x + (size_t)r * np + 2 * jp);
-        acc[r] = fma(a1.x, xv.x, acc[r]);
-        acc[r] = fma(a1.y, xv.y, acc[r]);
-        acc[8 + r] = fma(a2.x, xv.x, acc[8 + r]);
-        acc[8 + r] = fma(a2.y, xv.y, acc[8 + r]);
-      }
-    }
-    warp_reduce16(acc, lane);
-    if ((lane & 1) == 0) {
-      const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-      if (idx < 8) y1[(size_t)idx * np + i] = scale1 * acc[0];
-      else if (y2) y2[(size_t)(idx - 8) * np + i] = scale2 * acc[0];
-    }
-  }
+// ---- FP64 tensor-core contraction ------------------------------------------------------------
+// D[8x8] += A[8x4] B[4x8]; lane = 4*g + c holds a = A[g][c], b = B[c][g], c0/c1 = D[g][2c], D[g][2c+1].
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
 }
 
-// y[r][j] -= sum_i A[i][j] g[r][i]   (transposed product, A row-major [n][np]).
-// Thread owns a column pair and a slice of the rows; slices are combined in a fixed order
-// (deterministic, no atomics).  Contains __syncthreads(): call from all threads.
-__device__ __forceinline__ void matvec_cols_sub(const double* __restrict__ A, const double* g, double* y, int n,
-                                                int np) {
-  const int tid = threadIdx.x;
-  const int npair = np >> 1;
-  const int nsplit = npair < kThreads ? kThreads / npair : 1;
-  const int s = npair < kThreads ? tid / npair : 0;
-  const int jp0 = tid - s * npair;
-  if (nsplit == 1) {
-    for (int jp = tid; jp < npair; jp += kThreads) {
-      double acc[2][kCh];
-#pragma unroll
-      for (int r = 0; r < kCh; ++r) acc[0][r] = acc[1][r] = 0.0;
-      for (int i = 0; i < n; ++i) {
-        const double2 a = __ldg(reinterpret_cast<const double2*>(A + (size_t)i * np) + jp);
-#pragma unroll
-        for (int r = 0; r < kCh; ++r) {
-          const double gv = g[(size_t)r * np + i];
-          acc[0][r] = fma(a.x, gv, acc[0][r]);
-          acc[1][r] = fma(a.y, gv, acc[1][r]);
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < kCh; ++r) {
-        y[(size_t)r * np + 2 * jp] -= acc[0][r];
-        y[(size_t)r * np + 2 * jp + 1] -= acc[1][r];
-      }
-    }
-    __syncthreads();
-    return;
-  }
-  double acc[2][kCh];
-#pragma unroll
-  for (int r = 0; r < kCh; ++r) acc[0][r] = acc[1][r] = 0.0;
-  if (s < nsplit) {
-    for (int i = s; i < n; i += nsplit) {
-      const double2 a = __ldg(reinterpret_cast<const double2*>(A + (size_t)i * np) + jp0);
-#pragma unroll
-      for (int r = 0; r < kCh; ++r) {
-        const double gv = g[(size_t)r * np + i];
-        acc[0][r] = fma(a.x, gv, acc[0][r]);
-        acc[1][r] = fma(a.y, gv, acc[1][r]);
-      }
+// A matrix stream as seen by one lane.  Forward (y = A x, 8 output rows i0..i0+7): the lane walks row
+// i0 + g in 8-column steps, 16 B at columns 8s + 2c, 2c+1.  Transposed (y = A^T x, 8 output columns
+// j0..j0+7): column j0 + g, rows 8s + 2c and 8s + 2c + 1.  Either way step s contributes two k=4
+// contractions whose k-index c maps to vector element 8s + 2c (+1), i.e. the B fragments are the
+// 16 B at x[chain g][8s + 2c].
+struct MatStream {
+  const double* p;  // lane base pointer
+  int tr;           // 0 forward, 1 transposed
+};
+__device__ __forceinline__ MatStream stream_fwd(const double* A, int np, int blk, int lane) {
+  return MatStream{A + (size_t)(blk * 8 + (lane >> 2)) * np + 2 * (lane & 3), 0};
+}
+__device__ __forceinline__ MatStream stream_tr(const double* A, int np, int blk, int lane) {
+  return MatStream{A + (size_t)(2 * (lane & 3)) * np + blk * 8 + (lane >> 2), 1};
+}
+
+__device__ __forceinline__ double2 load_step(const MatStream st, int s, int nk8, int np) {
+  double2 v = make_double2(0.0, 0.0);
+  if (s < nk8) {
+    if (st.tr == 0) {
+      v = __ldg(reinterpret_cast<const double2*>(st.p + 8 * s));
+    } else {
+      v.x = __ldg(st.p + (size_t)(8 * s) * np);
+      v.y = __ldg(st.p + (size_t)(8 * s + 1) * np);
     }
   }
-  for (int ss = 0; ss < nsplit; ++ss) {
-    if (s == ss) {
+  return v;
+}
+
+__device__ __forceinline__ void load_batch(double2 (&a)[kU], const MatStream st, int nk8, int np) {
 #pragma unroll
-      for (int r = 0; r < kCh; ++r) {
-        y[(size_t)r * np + 2 * jp0] -= acc[0][r];
-        y[(size_t)r * np + 2 * jp0 + 1] -= acc[1][r];
+  for (int u = 0; u < kU; ++u) a[u] = load_step(st, u, nk8, np);
+}
+
+// One 8-row (or 8-column) block of a contraction with the 8 chain vectors x[8][ns]: a rolling
+// register pipeline.  On entry a[u] holds step u of `cur` (u < kU); every register is refilled with
+// step s + kU as soon as step s has been consumed, so kU 16-byte loads per lane stay in flight; at
+// the end of the block the refills switch to the warp's NEXT task `nxt` (possibly in a later phase,
+// behind a __syncthreads), whose first kU steps are therefore already in flight when it starts.
+// Result: c0, c1 = y[chain 2c], y[chain 2c+1] at block element g (lane = 4g + c).
+__device__ __forceinline__ void mma_task(double2 (&a)[kU], const MatStream cur, const MatStream nxt, bool has_next,
+                                         const double* x, int ns, int nk8, int np, double& c0, double& c1) {
+  const int lane = threadIdx.x & 31;
+  const double* bp = x + (size_t)(lane >> 2) * ns + 2 * (lane & 3);
+  const int nk8p = ((nk8 + kU - 1) / kU) * kU;  // steps rounded up to whole batches (extra ones are empty)
+  const int nk8n = has_next ? nk8 : 0;
+  double e0 = 0.0, e1 = 0.0, o0 = 0.0, o1 = 0.0;
+  for (int s0 = 0; s0 < nk8p; s0 += kU) {
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int s = s0 + u;
+      if (s < nk8) {
+        const double2 b = *reinterpret_cast<const double2*>(bp + 8 * s);
+        dmma(e0, e1, a[u].x, b.x);
+        dmma(o0, o1, a[u].y, b.y);
       }
+      const int sn = s + kU;
+      a[u] = sn < nk8p ? load_step(cur, sn, nk8, np) : load_step(nxt, sn - nk8p, nk8n, np);
     }
-    __syncthreads();
   }
+  c0 = e0 + o0;
+  c1 = e1 + o1;
 }
 
 // Per-chain transforms of the small state parts (magi_v2.py:318-319).  Threads 0..7.
@@ -225,52 +193,93 @@ __device__ __forceinline__ void chain_scalars(const Scratch<M>& S) {
 template <class M>
 __device__ void eval_logpost_grad(const Scratch<M>& S, const double* __restrict__ mats, double inv_beta) {
   constexpr int D = M::D, P = M::P, NRED = Scratch<M>::NRED;
-  const int n = S.n, np = S.np;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r = tid >> 6, l = tid & 63;  // pointwise phases: 64 threads per chain
+  const int n = S.n, np = S.np, ns = S.ns;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const ChainMap cm = chain_map();
+  const int r = cm.r;
   const size_t msz = (size_t)np * np;
+  const int nblk = np >> 3;  // 8-row blocks = 8-column steps
+  const int g = lane >> 2, c2 = 2 * (lane & 3);
 
   chain_scalars(S);
+  // first matrix batch of this warp goes in flight before anything else
+  double2 a[kU];
+  const bool active = warp < nblk;
+  if (active) load_batch(a, stream_fwd(mats, np, warp, lane), nblk, np);
   __syncthreads();
 
   double th[P];
 #pragma unroll
   for (int k = 0; k < P; ++k) th[k] = S.th[k * kCh + r];
 
-  // f(X, theta) at every grid point
-  for (int j = l; j < np; j += 64) {
+  // f(X, theta) at every grid point (padding stays zero: it is a B operand of the contractions)
+  for (int j = cm.j0; j < ns; j += cm.jstride) {
     double x[D], f[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) x[d] = S.Xc[S.vix(d, r, j)] + S.mu[d];
     M::f(x, th, f);
 #pragma unroll
-    for (int d = 0; d < D; ++d) S.FR[S.vix(d, r, j)] = j < n ? f[d] : 0.0;
+    for (int d = 0; d < D; ++d) S.FG[S.vix(d, r, j)] = j < n ? f[d] : 0.0;
   }
   __syncthreads();
 
-  double t1 = 0.0;
+  double t1 = 0.0, t2 = 0.0;
   for (int d = 0; d < D; ++d) {
     const double* SC = mats + (size_t)(3 * d + 0) * msz;
     const double* Mm = mats + (size_t)(3 * d + 1) * msz;
     const double* SK = mats + (size_t)(3 * d + 2) * msz;
     double* xc = S.Xc + S.vix(d, 0, 0);
-    double* fr = S.FR + S.vix(d, 0, 0);
-    double* g = S.G + S.vix(d, 0, 0);
+    double* fg = S.FG + S.vix(d, 0, 0);
     double* gx = S.GX + S.vix(d, 0, 0);
-    // gx = 2 S_C xc ; W = m xc
-    matvec_rows(SC, Mm, xc, gx, S.W, 2.0, 1.0, n, np);
-    __syncthreads();
-    for (int j = l; j < n; j += 64) {
-      const size_t a = (size_t)r * np + j;
-      t1 = fma(xc[a], 0.5 * gx[a], t1);
-      fr[a] -= S.W[a];
+    // pass 1: gx = 2 S_C xc ; W = m xc
+    for (int blk = warp; blk < nblk; blk += nw) {
+      double c0, c1;
+      const MatStream sm = stream_fwd(Mm, np, blk, lane);
+      mma_task(a, stream_fwd(SC, np, blk, lane), sm, true, xc, ns, nblk, np, c0, c1);
+      gx[(size_t)c2 * ns + blk * 8 + g] = 2.0 * c0;
+      gx[(size_t)(c2 + 1) * ns + blk * 8 + g] = 2.0 * c1;
+      const bool more = blk + nw < nblk;
+      const MatStream nx = more ? stream_fwd(SC, np, blk + nw, lane) : stream_fwd(SK, np, warp, lane);
+      mma_task(a, sm, nx, true, xc, ns, nblk, np, c0, c1);
+      S.W[(size_t)c2 * ns + blk * 8 + g] = c0;
+      S.W[(size_t)(c2 + 1) * ns + blk * 8 + g] = c1;
     }
     __syncthreads();
-    // g = 2 S_K r
-    matvec_rows(SK, nullptr, fr, g, nullptr, 2.0, 0.0, n, np);
+    for (int j = cm.j0; j < n; j += cm.jstride) {
+      const size_t e = (size_t)r * ns + j;
+      t1 = fma(xc[e], 0.5 * gx[e], t1);
+      fg[e] -= S.W[e];
+    }
     __syncthreads();
-    // gx -= m^T g
-    matvec_cols_sub(Mm, g, gx, n, np);  // ends with __syncthreads()
+    // pass 2: W = g = 2 S_K r
+    for (int blk = warp; blk < nblk; blk += nw) {
+      double c0, c1;
+      const bool more = blk + nw < nblk;
+      const MatStream nx = more ? stream_fwd(SK, np, blk + nw, lane) : stream_tr(Mm, np, warp, lane);
+      mma_task(a, stream_fwd(SK, np, blk, lane), nx, true, fg, ns, nblk, np, c0, c1);
+      S.W[(size_t)c2 * ns + blk * 8 + g] = 2.0 * c0;
+      S.W[(size_t)(c2 + 1) * ns + blk * 8 + g] = 2.0 * c1;
+    }
+    __syncthreads();
+    // pass 3: gx -= m^T g   (second read of m: an L2 hit)
+    for (int blk = warp; blk < nblk; blk += nw) {
+      double c0, c1;
+      const bool more = blk + nw < nblk;
+      const bool has = more || d + 1 < D;
+      const MatStream nx = more ? stream_tr(Mm, np, blk + nw, lane)
+                                : stream_fwd(mats + (size_t)(3 * (d + 1)) * msz, np, warp, lane);
+      mma_task(a, stream_tr(Mm, np, blk, lane), nx, has, S.W, ns, nblk, np, c0, c1);
+      gx[(size_t)c2 * ns + blk * 8 + g] -= c0;
+      gx[(size_t)(c2 + 1) * ns + blk * 8 + g] -= c1;
+    }
+    // t2 partial, and g_d takes the place of r_d (neither touches what pass 3 reads or writes)
+    for (int j = cm.j0; j < n; j += cm.jstride) {
+      const size_t e = (size_t)r * ns + j;
+      const double gv = S.W[e];
+      t2 = fma(fg[e], 0.5 * gv, t2);
+      fg[e] = gv;
+    }
+    __syncthreads();
   }
 
   // pointwise: ODE Jacobian terms, likelihood, assemble gradient
@@ -278,24 +287,24 @@ __device__ void eval_logpost_grad(const Scratch<M>& S, const double* __restrict_
 #pragma unroll
   for (int k = 0; k < NRED; ++k) red[k] = 0.0;
   red[0] = t1;
+  red[1] = t2;
   double isig2[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) isig2[d] = 1.0 / S.sig2[d * kCh + r];
-  for (int j = l; j < n; j += 64) {
-    double x[D], g[D], vx[D], vth[P];
+  for (int j = cm.j0; j < n; j += cm.jstride) {
+    double x[D], gg[D], vx[D], vth[P];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       x[d] = S.Xc[S.vix(d, r, j)] + S.mu[d];
-      g[d] = S.G[S.vix(d, r, j)];
-      red[1] = fma(S.FR[S.vix(d, r, j)], 0.5 * g[d], red[1]);
+      gg[d] = S.FG[S.vix(d, r, j)];
     }
-    M::vjp(x, th, g, vx, vth);
+    M::vjp(x, th, gg, vx, vth);
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       const double e = S.MK[d * np + j] != 0.0 ? x[d] - S.Y[d * np + j] : 0.0;
       red[2 + d] = fma(e, e, red[2 + d]);
-      const size_t a = S.vix(d, r, j);
-      S.GX[a] = -0.5 * ((S.GX[a] + vx[d]) * inv_beta + 2.0 * e * isig2[d]);
+      const size_t ai = S.vix(d, r, j);
+      S.GX[ai] = -0.5 * ((S.GX[ai] + vx[d]) * inv_beta + 2.0 * e * isig2[d]);
     }
 #pragma unroll
     for (int k = 0; k < P; ++k) red[2 + D + k] += vth[k];
@@ -307,10 +316,14 @@ __device__ void eval_logpost_grad(const Scratch<M>& S, const double* __restrict_
   }
   __syncthreads();
   if (tid < kCh) {
-    const int c = tid;  // chain; its two warps are 2c and 2c+1
+    const int c = tid;  // chain; its warps are c, c + 8, c + 16 (fixed summation order)
     double tot[NRED];
 #pragma unroll
-    for (int k = 0; k < NRED; ++k) tot[k] = S.wpart[(2 * c) * NRED + k] + S.wpart[(2 * c + 1) * NRED + k];
+    for (int k = 0; k < NRED; ++k) {
+      double v = 0.0;
+      for (int w = c; w < nw; w += 8) v += S.wpart[w * NRED + k];
+      tot[k] = v;
+    }
     double t3 = 0.0, t4 = 0.0, lj = 0.0;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
@@ -331,7 +344,7 @@ __device__ void eval_logpost_grad(const Scratch<M>& S, const double* __restrict_
   __syncthreads();
 }
 
-// Load the per-dataset constants and zero the padding of the vector arrays.
+// Load the per-dataset constants.
 template <class M>
 __device__ void load_dataset(const Scratch<M>& S, const magi_problem_t& pb, int b) {
   constexpr int D = M::D;
@@ -341,7 +354,7 @@ __device__ void load_dataset(const Scratch<M>& S, const magi_problem_t& pb, int 
     S.Nd[tid] = pb.N_ds[(size_t)b * D + tid];
     S.LB[tid] = pb.LB[(size_t)b * D + tid];
   }
-  for (int e = tid; e < D * np; e += kThreads) {
+  for (int e = tid; e < D * np; e += blockDim.x) {
     const int d = e / np, j = e - d * np;
     double yv = 0.0, mk = 0.0;
     if (j < n) {
@@ -360,12 +373,12 @@ template <class M>
 __device__ void load_state(const Scratch<M>& S, const double* X, const double* sig_pre, const double* th_pre,
                            size_t chain0, int nr) {
   constexpr int D = M::D, P = M::P;
-  const int n = S.n, np = S.np, tid = threadIdx.x;
-  const size_t tot = (size_t)D * kCh * np;
-  for (size_t e = tid; e < tot; e += kThreads) S.Xc[e] = 0.0;
+  const int n = S.n, tid = threadIdx.x;
+  for (size_t e = tid; e < 3 * S.vsize(); e += blockDim.x) S.Xc[e] = 0.0;  // Xc, FG, GX are contiguous
+  for (size_t e = tid; e < (size_t)kCh * S.ns; e += blockDim.x) S.W[e] = 0.0;
   __syncthreads();
   const int per = n * D;
-  for (int e = tid; e < nr * per; e += kThreads) {
+  for (int e = tid; e < nr * per; e += blockDim.x) {
     const int r = e / per, rem = e - r * per;
     const int j = rem / D, d = rem - j * D;
     S.Xc[S.vix(d, r, j)] = X[(chain0 + r) * per + rem] - S.mu[d];
@@ -374,8 +387,8 @@ __device__ void load_state(const Scratch<M>& S, const double* X, const double* s
     const int r = tid / D, d = tid - r * D;
     S.s[d * kCh + r] = r < nr ? sig_pre[(chain0 + r) * D + d] : 0.0;
   }
-  if (tid >= 64 && tid < 64 + kCh * P) {
-    const int t = tid - 64, r = t / P, k = t - r * P;
+  if (tid >= 128 && tid < 128 + kCh * P) {
+    const int t = tid - 128, r = t / P, k = t - r * P;
     S.tau[k * kCh + r] = r < nr ? th_pre[(chain0 + r) * P + k] : 0.0;
   }
 }

@@ -34,6 +34,13 @@ __global__ void pack_kernel(const double* __restrict__ Cinv, const double* __res
 // ------------------------------------------------------------------------------------------------
 // scratch placement: big vector arrays in shared memory when they fit, else in the workspace
 // ------------------------------------------------------------------------------------------------
+// one warp per 8-row block of the matrices, between 8 and 21 warps
+inline int threads_for(int n) {
+  const int nblk = magi_pad8(n) / 8;
+  const int nw = nblk < kMinWarps ? kMinWarps : (nblk > kMaxWarps ? kMaxWarps : nblk);
+  return 32 * nw;
+}
+
 template <class M>
 struct Placement {
   size_t smem_bytes;      // dynamic shared memory per CTA
@@ -51,7 +58,7 @@ Placement<M> placement(int n, bool with_momentum, bool with_save) {
   p.big_in_smem = big + small <= kMaxSmem;
   p.smem_bytes = p.big_in_smem ? big + small : small;
   p.ws_big_elems = p.big_in_smem ? 0 : Scratch<M>::big_elems(np, with_momentum);
-  p.ws_save_elems = with_save ? (size_t)2 * M::D * kCh * np : 0;
+  p.ws_save_elems = with_save ? (size_t)2 * M::D * kCh * magi_chain_stride(np) : 0;
   return p;
 }
 
@@ -74,7 +81,7 @@ __device__ __forceinline__ void setup_scratch(Scratch<M>& S, double* ws, size_t 
 // (3b) log-posterior + gradient
 // ------------------------------------------------------------------------------------------------
 template <class M>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kMaxThreads, 1)
 logpost_grad_kernel(magi_problem_t pb, const double* __restrict__ X, const double* __restrict__ sig_pre,
                     const double* __restrict__ th_pre, const double* __restrict__ beta_temp,
                     double* __restrict__ lp, double* __restrict__ gX, double* __restrict__ gsig,
@@ -96,7 +103,7 @@ logpost_grad_kernel(magi_problem_t pb, const double* __restrict__ X, const doubl
 
   // scale by the temperature and store in the reference layout
   const int per = n * D;
-  for (int e = tid; e < nr * per; e += kThreads) {
+  for (int e = tid; e < nr * per; e += blockDim.x) {
     const int r = e / per, rem = e - r * per;
     const int j = rem / D, d = rem - j * D;
     gX[(chain0 + r) * per + rem] = beta_temp[chain0 + r] * S.GX[S.vix(d, r, j)];
@@ -118,9 +125,11 @@ logpost_grad_kernel(magi_problem_t pb, const double* __restrict__ X, const doubl
 template <class M>
 __device__ __forceinline__ void kick(const Scratch<M>& S, const double* epsv, const double* btv, double c) {
   constexpr int D = M::D, P = M::P;
-  const int tid = threadIdx.x, r = tid >> 6, l = tid & 63;
+  const int tid = threadIdx.x;
+  const ChainMap cm = chain_map();
+  const int r = cm.r;
   const double h = c * epsv[r] * btv[r];
-  for (int j = l; j < S.n; j += 64) {
+  for (int j = cm.j0; j < S.n; j += cm.jstride) {
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       const size_t a = S.vix(d, r, j);
@@ -140,9 +149,11 @@ __device__ __forceinline__ void kick(const Scratch<M>& S, const double* epsv, co
 template <class M>
 __device__ __forceinline__ void drift(const Scratch<M>& S, const double* epsv) {
   constexpr int D = M::D, P = M::P;
-  const int tid = threadIdx.x, r = tid >> 6, l = tid & 63;
+  const int tid = threadIdx.x;
+  const ChainMap cm = chain_map();
+  const int r = cm.r;
   const double h = epsv[r];
-  for (int j = l; j < S.n; j += 64) {
+  for (int j = cm.j0; j < S.n; j += cm.jstride) {
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       const size_t a = S.vix(d, r, j);
@@ -178,9 +189,11 @@ __device__ void leapfrog_steps(const Scratch<M>& S, const double* mats, double i
 template <class M>
 __device__ void kinetic(const Scratch<M>& S, double* out) {
   constexpr int D = M::D, P = M::P;
-  const int tid = threadIdx.x, r = tid >> 6, l = tid & 63, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  const ChainMap cm = chain_map();
+  const int r = cm.r;
   double acc = 0.0;
-  for (int j = l; j < S.n; j += 64) {
+  for (int j = cm.j0; j < S.n; j += cm.jstride) {
 #pragma unroll
     for (int d = 0; d < D; ++d) {
       const double p = S.PX[S.vix(d, r, j)];
@@ -191,7 +204,8 @@ __device__ void kinetic(const Scratch<M>& S, double* out) {
   if (lane == 0) S.wpart[warp] = acc;
   __syncthreads();
   if (tid < kCh) {
-    double t = S.wpart[2 * tid] + S.wpart[2 * tid + 1];
+    double t = 0.0;
+    for (int w = tid; w < nw; w += 8) t += S.wpart[w];
 #pragma unroll
     for (int d = 0; d < D; ++d) t = fma(S.ps[d * kCh + tid], S.ps[d * kCh + tid], t);
 #pragma unroll
@@ -205,7 +219,7 @@ __device__ void kinetic(const Scratch<M>& S, double* out) {
 // (3c) leapfrog with caller-supplied momenta
 // ------------------------------------------------------------------------------------------------
 template <class M>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kMaxThreads, 1)
 leapfrog_kernel(magi_problem_t pb, double* X, double* sig_pre, double* th_pre, double* pX, double* psig,
                 double* pth, const double* __restrict__ eps, const double* __restrict__ beta_temp, int n_steps,
                 double* lp_out, double* ws, size_t ws_big) {
@@ -223,9 +237,9 @@ leapfrog_kernel(magi_problem_t pb, double* X, double* sig_pre, double* th_pre, d
   __syncthreads();
   load_state(S, X, sig_pre, th_pre, chain0, nr);
   const int per = n * D;
-  for (size_t e = tid; e < (size_t)D * kCh * np; e += kThreads) S.PX[e] = 0.0;
+  for (size_t e = tid; e < S.vsize(); e += blockDim.x) S.PX[e] = 0.0;
   __syncthreads();
-  for (int e = tid; e < nr * per; e += kThreads) {
+  for (int e = tid; e < nr * per; e += blockDim.x) {
     const int r = e / per, rem = e - r * per;
     const int j = rem / D, d = rem - j * D;
     S.PX[S.vix(d, r, j)] = pX[(chain0 + r) * per + rem];
@@ -245,7 +259,7 @@ leapfrog_kernel(magi_problem_t pb, double* X, double* sig_pre, double* th_pre, d
   eval_logpost_grad(S, mats, inv_beta);
   leapfrog_steps(S, mats, inv_beta, epsv, btv, n_steps);
 
-  for (int e = tid; e < nr * per; e += kThreads) {
+  for (int e = tid; e < nr * per; e += blockDim.x) {
     const int r = e / per, rem = e - r * per;
     const int j = rem / D, d = rem - j * D;
     X[(chain0 + r) * per + rem] = S.Xc[S.vix(d, r, j)] + S.mu[d];
@@ -274,7 +288,7 @@ struct HmcOut {
 };
 
 template <class M>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kMaxThreads, 1)
 hmc_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig_pre, double* th_pre, double* eps,
            double* da_state, HmcOut out, double* ws, size_t ws_big, size_t ws_save) {
   constexpr int D = M::D, P = M::P;
@@ -286,8 +300,9 @@ hmc_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig_pre,
   const size_t chain0 = (size_t)b * pb.R + r0;
   const size_t nchains = (size_t)pb.B * pb.R;
   const int n = S.n, np = S.np, tid = threadIdx.x;
-  const int r = tid >> 6, l = tid & 63;
-  const size_t v = (size_t)D * kCh * np;
+  const ChainMap cm = chain_map();
+  const int r = cm.r;
+  const size_t v = S.vsize();
   // control block in shared memory
   double* epsv = S.ctl;               // [8]
   double* btv = S.ctl + 1 * kCh;      // [8]
@@ -324,7 +339,7 @@ hmc_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig_pre,
     const double bt = cfg.fixed_beta_temp > 0.0 ? cfg.fixed_beta_temp
                                                 : fmax(1.0 / log((double)git + 2.0), cfg.min_temp);
     // save the start point and its gradient
-    for (int j = l; j < n; j += 64) {
+    for (int j = cm.j0; j < n; j += cm.jstride) {
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         const size_t a = S.vix(d, r, j);
@@ -343,7 +358,7 @@ hmc_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig_pre,
     // momenta ~ N(0, I): element e of the packed state (X row-major [n][D], then s, then tau)
     if (r < nr) {
       const uint32_t cid = cfg.chain_id0 + (uint32_t)(chain0 + r);
-      for (int q = l; q < npairs; q += 64) {
+      for (int q = cm.j0; q < npairs; q += cm.jstride) {
         double z[2];
         magi_normal_pair(cfg.seed, (uint32_t)q, cid, (uint32_t)git, z[0], z[1]);
 #pragma unroll
@@ -417,7 +432,7 @@ hmc_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig_pre,
     // rejected chains go back to the start point; then emit the trajectory sample
     const bool acc = accf[r] != 0.0;
     const bool accum = git >= cfg.accum_from && (out.X_sum || out.X_sumsq);
-    for (int j = l; j < n; j += 64) {
+    for (int j = cm.j0; j < n; j += cm.jstride) {
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         const size_t a = S.vix(d, r, j);
@@ -441,7 +456,7 @@ hmc_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig_pre,
 
   // write back the chain state
   const int per = n * D;
-  for (int e = tid; e < nr * per; e += kThreads) {
+  for (int e = tid; e < nr * per; e += blockDim.x) {
     const int rr = e / per, rem = e - rr * per;
     const int j = rem / D, d = rem - j * D;
     X[(chain0 + rr) * per + rem] = S.Xc[S.vix(d, rr, j)] + S.mu[d];
@@ -488,7 +503,7 @@ int launch_logpost(const magi_problem_t* pb, const double* X, const double* sig_
   cudaError_t e = cudaFuncSetAttribute(logpost_grad_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)p.smem_bytes);
   if (e != cudaSuccess) return magi_cuda_status(e);
-  logpost_grad_kernel<M><<<grid, kThreads, p.smem_bytes, st>>>(*pb, X, sig_pre, th_pre, beta_temp, lp, gX, gsig,
+  logpost_grad_kernel<M><<<grid, threads_for(pb->n), p.smem_bytes, st>>>(*pb, X, sig_pre, th_pre, beta_temp, lp, gX, gsig,
                                                                gth, static_cast<double*>(ws), p.ws_big_elems);
   return magi_cuda_status(cudaGetLastError());
 }
@@ -503,7 +518,7 @@ int launch_leapfrog(const magi_problem_t* pb, double* X, double* sig_pre, double
   cudaError_t e = cudaFuncSetAttribute(leapfrog_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)p.smem_bytes);
   if (e != cudaSuccess) return magi_cuda_status(e);
-  leapfrog_kernel<M><<<grid, kThreads, p.smem_bytes, st>>>(*pb, X, sig_pre, th_pre, pX, psig, pth, eps, beta_temp,
+  leapfrog_kernel<M><<<grid, threads_for(pb->n), p.smem_bytes, st>>>(*pb, X, sig_pre, th_pre, pX, psig, pth, eps, beta_temp,
                                                            n_steps, lp_out, static_cast<double*>(ws),
                                                            p.ws_big_elems);
   return magi_cuda_status(cudaGetLastError());
@@ -520,7 +535,7 @@ int launch_hmc(const magi_problem_t* pb, const magi_hmc_config_t* cfg, double* X
   cudaError_t e =
       cudaFuncSetAttribute(hmc_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
   if (e != cudaSuccess) return magi_cuda_status(e);
-  hmc_kernel<M><<<grid, kThreads, p.smem_bytes, st>>>(*pb, *cfg, X, sig_pre, th_pre, eps, da_state, out,
+  hmc_kernel<M><<<grid, threads_for(pb->n), p.smem_bytes, st>>>(*pb, *cfg, X, sig_pre, th_pre, eps, da_state, out,
                                                       static_cast<double*>(ws), p.ws_big_elems, p.ws_save_elems);
   return magi_cuda_status(cudaGetLastError());
 }
