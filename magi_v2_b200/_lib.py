@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmagi_b200.so")
+LIB_PATH = os.environ.get("MAGI_B200_LIB", os.path.join(HERE, "libmagi_b200.so"))   # override: kernel experiments
 
 ABI_VERSION = 1
 MODEL_IDS = {"seir3": 0, "seir4": 1, "sirw": 2, "lorenz96": 3}

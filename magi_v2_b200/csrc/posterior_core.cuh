@@ -22,7 +22,13 @@ constexpr int kMaxWarps = 21;               // 672 threads: 96 registers per thr
 constexpr int kMaxThreads = kMaxWarps * 32;
 constexpr int kMinWarps = 8;                // pointwise phases map warp w to chain w % 8
 constexpr int kCh = MAGI_CHAINS_PER_CTA;    // 8
-constexpr int kU = 7;                       // 8-column steps per register batch (7 x 16 B per lane in flight)
+#ifndef MAGI_KU
+#define MAGI_KU 7
+#endif
+#ifndef MAGI_LDG_MODE
+#define MAGI_LDG_MODE 0   // 0: ld.global.nc  1: ld.global.nc.L1::no_allocate  2: ld.global.cg
+#endif
+constexpr int kU = MAGI_KU;                 // 8-column steps per register batch (kU x 16 B per lane in flight)
 
 // chain stride of the shared-memory vector arrays: np + 2 doubles, so that the 128-bit B-fragment
 // loads of a quarter warp (2 chains x 4 column pairs) fall into 32 distinct banks
@@ -34,7 +40,7 @@ struct Scratch {
   int n, np, ns;
   double *Xc, *FG, *GX;      // [D][8][ns]   centred state | f -> residual r -> g = 2 S_K r | gradient
   double* PX;                // [D][8][ns]   momentum (HMC kernels only; else nullptr)
-  double* W;                 // [8][ns]      m_d xc_d, then g_d
+  double *Wa0, *Wa1, *Wb;        // [8][ns] x3   m_d xc_d (double-buffered over d) and g_d = 2 S_K r_d
   double *Y, *MK;            // [D][np]      observations / mask as 0.0 or 1.0
   double *tau, *th, *sgt;    // [P][8]       theta_pre, softplus, sigmoid
   double *s, *sig2, *sgs;    // [D][8]       sigma_pre, softplus + LB, sigmoid
@@ -43,16 +49,17 @@ struct Scratch {
   double* L;                 // [8]          base log-posterior
   double *mu, *Nd, *LB;      // [D]
   double* wpart;             // [kMaxWarps][NRED]
+  double* wt1;               // [kMaxWarps][8]  per-warp partial sums of t1
   double* ctl;               // [kCtl][8]    sampler control values (step size, energies, saved small state)
   static constexpr int kCtl = 16 + 2 * M::P + 2 * M::D;
   static constexpr int NRED = 2 + M::D + M::P;
 
   __host__ __device__ static size_t big_elems(int np, bool with_momentum) {
-    return (size_t)(with_momentum ? 4 : 3) * M::D * kCh * magi_chain_stride(np) + (size_t)kCh * magi_chain_stride(np);
+    return (size_t)(with_momentum ? 4 : 3) * M::D * kCh * magi_chain_stride(np) + (size_t)3 * kCh * magi_chain_stride(np);
   }
   __host__ __device__ static size_t small_elems(int np) {
     const size_t e = (size_t)2 * M::D * np + (size_t)kCh * (5 * M::P + 5 * M::D + 1 + kCtl) + 3 * M::D +
-                     (size_t)kMaxWarps * NRED;
+                     (size_t)kMaxWarps * (NRED + kCh);
     return (e + 1) & ~(size_t)1;  // keep the big arrays behind it 16-byte aligned (128-bit loads)
   }
   __device__ void carve(double* big, double* small, int n_, int np_, bool with_momentum) {
@@ -64,7 +71,7 @@ struct Scratch {
     double* p = GX + v;
     PX = nullptr;
     if (with_momentum) { PX = p; p += v; }
-    W = p;
+    Wa0 = p; Wa1 = p + (size_t)kCh * ns; Wb = p + (size_t)2 * kCh * ns;
     p = small;
     Y = p; p += M::D * np;
     MK = p; p += M::D * np;
@@ -75,7 +82,22 @@ struct Scratch {
     L = p; p += kCh;
     mu = p; p += M::D; Nd = p; p += M::D; LB = p; p += M::D;
     wpart = p; p += kMaxWarps * NRED;
+    wt1 = p; p += kMaxWarps * kCh;
     ctl = p;
+  }
+  // Tell the compiler that every scratch pointer is a shared-memory address (LDS/STS instead of
+  // generic loads).  Only valid when the big arrays were carved out of shared memory too.
+  __device__ __forceinline__ void assume_shared() const {
+#define MAGI_ASSUME_SHARED(q) __builtin_assume(__isShared(q))
+    MAGI_ASSUME_SHARED(Xc); MAGI_ASSUME_SHARED(FG); MAGI_ASSUME_SHARED(GX); MAGI_ASSUME_SHARED(Wa0);
+    MAGI_ASSUME_SHARED(Wa1); MAGI_ASSUME_SHARED(Wb); MAGI_ASSUME_SHARED(Y); MAGI_ASSUME_SHARED(MK);
+    MAGI_ASSUME_SHARED(tau); MAGI_ASSUME_SHARED(th); MAGI_ASSUME_SHARED(sgt); MAGI_ASSUME_SHARED(s);
+    MAGI_ASSUME_SHARED(sig2); MAGI_ASSUME_SHARED(sgs); MAGI_ASSUME_SHARED(ptau); MAGI_ASSUME_SHARED(ps);
+    MAGI_ASSUME_SHARED(gtau); MAGI_ASSUME_SHARED(gs); MAGI_ASSUME_SHARED(L); MAGI_ASSUME_SHARED(mu);
+    MAGI_ASSUME_SHARED(Nd); MAGI_ASSUME_SHARED(LB); MAGI_ASSUME_SHARED(wpart); MAGI_ASSUME_SHARED(wt1);
+    MAGI_ASSUME_SHARED(ctl);
+    if (PX) MAGI_ASSUME_SHARED(PX);
+#undef MAGI_ASSUME_SHARED
   }
   __device__ __forceinline__ size_t vix(int d, int r, int j) const { return ((size_t)d * kCh + r) * ns + j; }
   __device__ __forceinline__ size_t vsize() const { return (size_t)M::D * kCh * ns; }
@@ -103,68 +125,111 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
-// A matrix stream as seen by one lane.  Forward (y = A x, 8 output rows i0..i0+7): the lane walks row
-// i0 + g in 8-column steps, 16 B at columns 8s + 2c, 2c+1.  Transposed (y = A^T x, 8 output columns
-// j0..j0+7): column j0 + g, rows 8s + 2c and 8s + 2c + 1.  Either way step s contributes two k=4
-// contractions whose k-index c maps to vector element 8s + 2c (+1), i.e. the B fragments are the
+// A matrix stream as seen by one lane.  Forward (TR = 0; y = A x, 8 output rows i0..i0+7): the lane walks
+// row i0 + g in 8-column steps, 16 B at columns 8s + 2c, 2c+1.  Transposed (TR = 1; y = A^T x, 8 output
+// columns j0..j0+7): column j0 + g, rows 8s + 2c and 8s + 2c + 1.  Either way step s contributes two
+// k=4 contractions whose k-index c maps to vector element 8s + 2c (+1), i.e. the B fragments are the
 // 16 B at x[chain g][8s + 2c].
-struct MatStream {
-  const double* p;  // lane base pointer
-  int tr;           // 0 forward, 1 transposed
-};
-__device__ __forceinline__ MatStream stream_fwd(const double* A, int np, int blk, int lane) {
-  return MatStream{A + (size_t)(blk * 8 + (lane >> 2)) * np + 2 * (lane & 3), 0};
-}
-__device__ __forceinline__ MatStream stream_tr(const double* A, int np, int blk, int lane) {
-  return MatStream{A + (size_t)(2 * (lane & 3)) * np + blk * 8 + (lane >> 2), 1};
+constexpr int kFwd = 0, kTr = 1, kNone = -1;
+
+template <int TR>
+__device__ __forceinline__ const double* stream_ptr(const double* A, int np, int blk, int lane) {
+  return TR == kTr ? A + (size_t)(2 * (lane & 3)) * np + blk * 8 + (lane >> 2)
+                   : A + (size_t)(blk * 8 + (lane >> 2)) * np + 2 * (lane & 3);
 }
 
-__device__ __forceinline__ double2 load_step(const MatStream st, int s, int nk8, int np) {
+__device__ __forceinline__ double2 ldg_f64x2(const double* p) {
+#if MAGI_LDG_MODE == 1
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+#elif MAGI_LDG_MODE == 2
+  double2 v;
+  asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+#else
+  return __ldg(reinterpret_cast<const double2*>(p));
+#endif
+}
+__device__ __forceinline__ double ldg_f64(const double* p) {
+#if MAGI_LDG_MODE == 1
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+#elif MAGI_LDG_MODE == 2
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+
+// step s of a stream (zero beyond the last step)
+template <int TR>
+__device__ __forceinline__ double2 load_step(const double* p, int s, int nk8, int np) {
   double2 v = make_double2(0.0, 0.0);
   if (s < nk8) {
-    if (st.tr == 0) {
-      v = __ldg(reinterpret_cast<const double2*>(st.p + 8 * s));
+    if (TR == kTr) {
+      v.x = ldg_f64(p + (size_t)(8 * s) * np);
+      v.y = ldg_f64(p + (size_t)(8 * s + 1) * np);
     } else {
-      v.x = __ldg(st.p + (size_t)(8 * s) * np);
-      v.y = __ldg(st.p + (size_t)(8 * s + 1) * np);
+      v = ldg_f64x2(p + 8 * s);
     }
   }
   return v;
 }
 
-__device__ __forceinline__ void load_batch(double2 (&a)[kU], const MatStream st, int nk8, int np) {
+template <int TR>
+__device__ __forceinline__ void load_batch(double2 (&a)[kU], const double* p, int nk8, int np) {
 #pragma unroll
-  for (int u = 0; u < kU; ++u) a[u] = load_step(st, u, nk8, np);
+  for (int u = 0; u < kU; ++u) a[u] = load_step<TR>(p, u, nk8, np);
 }
 
-// One 8-row (or 8-column) block of a contraction with the 8 chain vectors x[8][ns]: a rolling
-// register pipeline.  On entry a[u] holds step u of `cur` (u < kU); every register is refilled with
-// step s + kU as soon as step s has been consumed, so kU 16-byte loads per lane stay in flight; at
-// the end of the block the refills switch to the warp's NEXT task `nxt` (possibly in a later phase,
-// behind a __syncthreads), whose first kU steps are therefore already in flight when it starts.
+// One 8-row (CT = kFwd) or 8-column (CT = kTr) block of a contraction with the 8 chain vectors x[8][ns]
+// (or x - xsub when SUB): a rolling register pipeline.  On entry a[u] holds step u of the current stream
+// `cp` (u < kU); every register is refilled with step s + kU as soon as step s has been consumed, so kU
+// 16-byte loads per lane stay in flight; during the last batch the refills switch to the warp's NEXT
+// task `np_` of kind NT (possibly in a later phase, behind a __syncthreads; nullptr or NT = kNone: no
+// next task), whose first kU steps are therefore already in flight when it starts.
 // Result: c0, c1 = y[chain 2c], y[chain 2c+1] at block element g (lane = 4g + c).
-__device__ __forceinline__ void mma_task(double2 (&a)[kU], const MatStream cur, const MatStream nxt, bool has_next,
-                                         const double* x, int ns, int nk8, int np, double& c0, double& c1) {
+template <bool SUB, int CT, int NT>
+__device__ __forceinline__ void mma_task(double2 (&a)[kU], const double* cp, const double* nxp, const double* x,
+                                         const double* xsub, int ns, int nk8, int np, double& c0, double& c1) {
   const int lane = threadIdx.x & 31;
-  const double* bp = x + (size_t)(lane >> 2) * ns + 2 * (lane & 3);
-  const int nk8p = ((nk8 + kU - 1) / kU) * kU;  // steps rounded up to whole batches (extra ones are empty)
-  const int nk8n = has_next ? nk8 : 0;
-  double e0 = 0.0, e1 = 0.0, o0 = 0.0, o1 = 0.0;
-  for (int s0 = 0; s0 < nk8p; s0 += kU) {
+  const size_t bo = (size_t)(lane >> 2) * ns + 2 * (lane & 3);
+  const double* bp = x + bo;
+  const double* bs = SUB ? xsub + bo : nullptr;
+  const int nlast = ((nk8 - 1) / kU) * kU;  // first step of the last batch
+  double acc[4][2];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = 0.0;
+  auto consume = [&](int s, int u) {
+    double2 b = *reinterpret_cast<const double2*>(bp + 8 * s);
+    if (SUB) {
+      const double2 b2 = *reinterpret_cast<const double2*>(bs + 8 * s);
+      b.x -= b2.x;
+      b.y -= b2.y;
+    }
+    dmma(acc[(2 * u) & 3][0], acc[(2 * u) & 3][1], a[u].x, b.x);
+    dmma(acc[(2 * u + 1) & 3][0], acc[(2 * u + 1) & 3][1], a[u].y, b.y);
+  };
+#pragma unroll 1
+  for (int s0 = 0; s0 < nlast; s0 += kU) {
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const int s = s0 + u;
-      if (s < nk8) {
-        const double2 b = *reinterpret_cast<const double2*>(bp + 8 * s);
-        dmma(e0, e1, a[u].x, b.x);
-        dmma(o0, o1, a[u].y, b.y);
-      }
-      const int sn = s + kU;
-      a[u] = sn < nk8p ? load_step(cur, sn, nk8, np) : load_step(nxt, sn - nk8p, nk8n, np);
+      consume(s0 + u, u);
+      a[u] = load_step<CT>(cp, s0 + u + kU, nk8, np);
     }
   }
-  c0 = e0 + o0;
-  c1 = e1 + o1;
+  const int nnext = (NT != kNone && nxp != nullptr) ? nk8 : 0;
+#pragma unroll
+  for (int u = 0; u < kU; ++u) {
+    if (nlast + u < nk8) consume(nlast + u, u);
+    a[u] = load_step<(NT == kNone ? kFwd : NT)>(nxp, u, nnext, np);
+  }
+  c0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+  c1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
 }
 
 // Per-chain transforms of the small state parts (magi_v2.py:318-319).  Threads 0..7.
@@ -205,7 +270,7 @@ __device__ void eval_logpost_grad(const Scratch<M>& S, const double* __restrict_
   // first matrix batch of this warp goes in flight before anything else
   double2 a[kU];
   const bool active = warp < nblk;
-  if (active) load_batch(a, stream_fwd(mats, np, warp, lane), nblk, np);
+  if (active) load_batch<kFwd>(a, stream_ptr<kFwd>(mats, np, warp, lane), nblk, np);
   __syncthreads();
 
   double th[P];
@@ -223,60 +288,73 @@ __device__ void eval_logpost_grad(const Scratch<M>& S, const double* __restrict_
   }
   __syncthreads();
 
-  double t1 = 0.0, t2 = 0.0;
-  for (int d = 0; d < D; ++d) {
+  // Phases per component d (two barriers each):
+  //   A(d): u = 2 S_C xc -> GX_d ; w = m xc -> Wa[d&1]                      (A(0) alone, else merged into C(d-1))
+  //   B(d): g = 2 S_K (f - w) -> Wb        (the residual r = f - w is formed on the fly as the B operand)
+  //   C(d): GX_d -= m^T g (second read of m: L2) | t1, t2 partial sums, FG_d <- g | A(d+1)
+  double t1a = 0.0, t1b = 0.0, t2 = 0.0;
+  auto pass_a = [&](int d, bool chain_next) {
     const double* SC = mats + (size_t)(3 * d + 0) * msz;
     const double* Mm = mats + (size_t)(3 * d + 1) * msz;
     const double* SK = mats + (size_t)(3 * d + 2) * msz;
-    double* xc = S.Xc + S.vix(d, 0, 0);
-    double* fg = S.FG + S.vix(d, 0, 0);
+    const double* xc = S.Xc + S.vix(d, 0, 0);
     double* gx = S.GX + S.vix(d, 0, 0);
-    // pass 1: gx = 2 S_C xc ; W = m xc
+    double* wa = (d & 1) ? S.Wa1 : S.Wa0;
     for (int blk = warp; blk < nblk; blk += nw) {
       double c0, c1;
-      const MatStream sm = stream_fwd(Mm, np, blk, lane);
-      mma_task(a, stream_fwd(SC, np, blk, lane), sm, true, xc, ns, nblk, np, c0, c1);
+      const double* sm = stream_ptr<kFwd>(Mm, np, blk, lane);
+      mma_task<false, kFwd, kFwd>(a, stream_ptr<kFwd>(SC, np, blk, lane), sm, xc, nullptr, ns, nblk, np, c0, c1);
       gx[(size_t)c2 * ns + blk * 8 + g] = 2.0 * c0;
       gx[(size_t)(c2 + 1) * ns + blk * 8 + g] = 2.0 * c1;
+      t1a = fma(xc[(size_t)c2 * ns + blk * 8 + g], c0, t1a);  // xc . S_C xc for chains 2c, 2c+1
+      t1b = fma(xc[(size_t)(c2 + 1) * ns + blk * 8 + g], c1, t1b);
       const bool more = blk + nw < nblk;
-      const MatStream nx = more ? stream_fwd(SC, np, blk + nw, lane) : stream_fwd(SK, np, warp, lane);
-      mma_task(a, sm, nx, true, xc, ns, nblk, np, c0, c1);
-      S.W[(size_t)c2 * ns + blk * 8 + g] = c0;
-      S.W[(size_t)(c2 + 1) * ns + blk * 8 + g] = c1;
+      const double* nx = more ? stream_ptr<kFwd>(SC, np, blk + nw, lane)
+                              : (chain_next ? stream_ptr<kFwd>(SK, np, warp, lane) : nullptr);
+      mma_task<false, kFwd, kFwd>(a, sm, nx, xc, nullptr, ns, nblk, np, c0, c1);
+      wa[(size_t)c2 * ns + blk * 8 + g] = c0;
+      wa[(size_t)(c2 + 1) * ns + blk * 8 + g] = c1;
     }
-    __syncthreads();
-    for (int j = cm.j0; j < n; j += cm.jstride) {
-      const size_t e = (size_t)r * ns + j;
-      t1 = fma(xc[e], 0.5 * gx[e], t1);
-      fg[e] -= S.W[e];
-    }
-    __syncthreads();
-    // pass 2: W = g = 2 S_K r
+  };
+  pass_a(0, true);
+  __syncthreads();
+  for (int d = 0; d < D; ++d) {
+    const double* Mm = mats + (size_t)(3 * d + 1) * msz;
+    const double* SK = mats + (size_t)(3 * d + 2) * msz;
+    double* fg = S.FG + S.vix(d, 0, 0);
+    double* gx = S.GX + S.vix(d, 0, 0);
+    const double* wa = (d & 1) ? S.Wa1 : S.Wa0;
+    // B(d)
     for (int blk = warp; blk < nblk; blk += nw) {
       double c0, c1;
-      const bool more = blk + nw < nblk;
-      const MatStream nx = more ? stream_fwd(SK, np, blk + nw, lane) : stream_tr(Mm, np, warp, lane);
-      mma_task(a, stream_fwd(SK, np, blk, lane), nx, true, fg, ns, nblk, np, c0, c1);
-      S.W[(size_t)c2 * ns + blk * 8 + g] = 2.0 * c0;
-      S.W[(size_t)(c2 + 1) * ns + blk * 8 + g] = 2.0 * c1;
+      const double* cur = stream_ptr<kFwd>(SK, np, blk, lane);
+      if (blk + nw < nblk)
+        mma_task<true, kFwd, kFwd>(a, cur, stream_ptr<kFwd>(SK, np, blk + nw, lane), fg, wa, ns, nblk, np, c0, c1);
+      else
+        mma_task<true, kFwd, kTr>(a, cur, stream_ptr<kTr>(Mm, np, warp, lane), fg, wa, ns, nblk, np, c0, c1);
+      S.Wb[(size_t)c2 * ns + blk * 8 + g] = 2.0 * c0;
+      S.Wb[(size_t)(c2 + 1) * ns + blk * 8 + g] = 2.0 * c1;
     }
     __syncthreads();
-    // pass 3: gx -= m^T g   (second read of m: an L2 hit)
+    // C(d)
     for (int blk = warp; blk < nblk; blk += nw) {
       double c0, c1;
-      const bool more = blk + nw < nblk;
-      const bool has = more || d + 1 < D;
-      const MatStream nx = more ? stream_tr(Mm, np, blk + nw, lane)
-                                : stream_fwd(mats + (size_t)(3 * (d + 1)) * msz, np, warp, lane);
-      mma_task(a, stream_tr(Mm, np, blk, lane), nx, has, S.W, ns, nblk, np, c0, c1);
+      const double* cur = stream_ptr<kTr>(Mm, np, blk, lane);
+      if (blk + nw < nblk)
+        mma_task<false, kTr, kTr>(a, cur, stream_ptr<kTr>(Mm, np, blk + nw, lane), S.Wb, nullptr, ns, nblk, np, c0, c1);
+      else
+        mma_task<false, kTr, kFwd>(a, cur,
+                                   d + 1 < D ? stream_ptr<kFwd>(mats + (size_t)(3 * (d + 1)) * msz, np, warp, lane)
+                                             : nullptr,
+                                   S.Wb, nullptr, ns, nblk, np, c0, c1);
       gx[(size_t)c2 * ns + blk * 8 + g] -= c0;
       gx[(size_t)(c2 + 1) * ns + blk * 8 + g] -= c1;
     }
-    // t2 partial, and g_d takes the place of r_d (neither touches what pass 3 reads or writes)
+    if (d + 1 < D) pass_a(d + 1, true);
     for (int j = cm.j0; j < n; j += cm.jstride) {
       const size_t e = (size_t)r * ns + j;
-      const double gv = S.W[e];
-      t2 = fma(fg[e], 0.5 * gv, t2);
+      const double gv = S.Wb[e];
+      t2 = fma(fg[e] - wa[e], 0.5 * gv, t2);
       fg[e] = gv;
     }
     __syncthreads();
@@ -286,8 +364,14 @@ __device__ void eval_logpost_grad(const Scratch<M>& S, const double* __restrict_
   double red[NRED];
 #pragma unroll
   for (int k = 0; k < NRED; ++k) red[k] = 0.0;
-  red[0] = t1;
   red[1] = t2;
+  // t1: lanes hold partial sums for chains 2c, 2c+1 over their block rows g; fold the 8 values of g
+  t1a += magi_shfl_xor(t1a, 4); t1a += magi_shfl_xor(t1a, 8); t1a += magi_shfl_xor(t1a, 16);
+  t1b += magi_shfl_xor(t1b, 4); t1b += magi_shfl_xor(t1b, 8); t1b += magi_shfl_xor(t1b, 16);
+  if (lane < 4) {
+    S.wt1[warp * kCh + 2 * lane] = t1a;
+    S.wt1[warp * kCh + 2 * lane + 1] = t1b;
+  }
   double isig2[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) isig2[d] = 1.0 / S.sig2[d * kCh + r];
@@ -323,6 +407,11 @@ __device__ void eval_logpost_grad(const Scratch<M>& S, const double* __restrict_
       double v = 0.0;
       for (int w = c; w < nw; w += 8) v += S.wpart[w * NRED + k];
       tot[k] = v;
+    }
+    {
+      double v = 0.0;
+      for (int w = 0; w < nw; ++w) v += S.wt1[w * kCh + c];
+      tot[0] = v;
     }
     double t3 = 0.0, t4 = 0.0, lj = 0.0;
 #pragma unroll
@@ -375,7 +464,7 @@ __device__ void load_state(const Scratch<M>& S, const double* X, const double* s
   constexpr int D = M::D, P = M::P;
   const int n = S.n, tid = threadIdx.x;
   for (size_t e = tid; e < 3 * S.vsize(); e += blockDim.x) S.Xc[e] = 0.0;  // Xc, FG, GX are contiguous
-  for (size_t e = tid; e < (size_t)kCh * S.ns; e += blockDim.x) S.W[e] = 0.0;
+  for (size_t e = tid; e < (size_t)3 * kCh * S.ns; e += blockDim.x) S.Wa0[e] = 0.0;
   __syncthreads();
   const int per = n * D;
   for (int e = tid; e < nr * per; e += blockDim.x) {

@@ -5,6 +5,8 @@
 
 namespace {
 
+#include "sampler_fast.cuh"
+
 constexpr size_t kMaxSmem = 227 * 1024;
 
 // ------------------------------------------------------------------------------------------------
@@ -62,17 +64,20 @@ Placement<M> placement(int n, bool with_momentum, bool with_save) {
   return p;
 }
 
-template <class M>
+// SMEM = true: the vector arrays are carved out of dynamic shared memory (compile-time known, so the
+// compiler emits LDS/STS rather than generic loads); false: they live in the caller's workspace.
+template <class M, bool SMEM>
 __device__ __forceinline__ void setup_scratch(Scratch<M>& S, double* ws, size_t ws_big, size_t ws_save, int n,
                                               bool with_momentum, double*& save) {
   extern __shared__ __align__(16) double smem[];
   const int np = magi_pad8(n);
   const size_t cta = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
   double* wsc = ws ? ws + cta * (ws_big + ws_save) : nullptr;
-  if (ws_big) {
-    S.carve(wsc, smem, n, np, with_momentum);
-  } else {
+  if (SMEM) {
     S.carve(smem + Scratch<M>::small_elems(np), smem, n, np, with_momentum);
+    S.assume_shared();
+  } else {
+    S.carve(wsc, smem, n, np, with_momentum);
   }
   save = ws_save ? wsc + ws_big : nullptr;
 }
@@ -80,7 +85,7 @@ __device__ __forceinline__ void setup_scratch(Scratch<M>& S, double* ws, size_t 
 // ------------------------------------------------------------------------------------------------
 // (3b) log-posterior + gradient
 // ------------------------------------------------------------------------------------------------
-template <class M>
+template <class M, bool SMEM>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 logpost_grad_kernel(magi_problem_t pb, const double* __restrict__ X, const double* __restrict__ sig_pre,
                     const double* __restrict__ th_pre, const double* __restrict__ beta_temp,
@@ -89,7 +94,7 @@ logpost_grad_kernel(magi_problem_t pb, const double* __restrict__ X, const doubl
   constexpr int D = M::D, P = M::P;
   Scratch<M> S;
   double* save;
-  setup_scratch(S, ws, ws_big, 0, pb.n, false, save);
+  setup_scratch<M, SMEM>(S, ws, ws_big, 0, pb.n, false, save);
   const int b = blockIdx.y, r0 = blockIdx.x * kCh;
   const int nr = min(kCh, pb.R - r0);
   const size_t chain0 = (size_t)b * pb.R + r0;
@@ -218,7 +223,7 @@ __device__ void kinetic(const Scratch<M>& S, double* out) {
 // ------------------------------------------------------------------------------------------------
 // (3c) leapfrog with caller-supplied momenta
 // ------------------------------------------------------------------------------------------------
-template <class M>
+template <class M, bool SMEM>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 leapfrog_kernel(magi_problem_t pb, double* X, double* sig_pre, double* th_pre, double* pX, double* psig,
                 double* pth, const double* __restrict__ eps, const double* __restrict__ beta_temp, int n_steps,
@@ -226,7 +231,7 @@ leapfrog_kernel(magi_problem_t pb, double* X, double* sig_pre, double* th_pre, d
   constexpr int D = M::D, P = M::P;
   Scratch<M> S;
   double* save;
-  setup_scratch(S, ws, ws_big, 0, pb.n, true, save);
+  setup_scratch<M, SMEM>(S, ws, ws_big, 0, pb.n, true, save);
   const int b = blockIdx.y, r0 = blockIdx.x * kCh;
   const int nr = min(kCh, pb.R - r0);
   const size_t chain0 = (size_t)b * pb.R + r0;
@@ -283,18 +288,14 @@ leapfrog_kernel(magi_problem_t pb, double* X, double* sig_pre, double* th_pre, d
 // ------------------------------------------------------------------------------------------------
 // (3d) HMC sampler: all iterations of a group of 8 chains in one launch
 // ------------------------------------------------------------------------------------------------
-struct HmcOut {
-  double *th_samps, *sig_samps, *X_samps, *X_sum, *X_sumsq, *accept_prob, *lp_trace;
-};
-
-template <class M>
+template <class M, bool SMEM>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 hmc_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig_pre, double* th_pre, double* eps,
            double* da_state, HmcOut out, double* ws, size_t ws_big, size_t ws_save) {
   constexpr int D = M::D, P = M::P;
   Scratch<M> S;
   double* save;
-  setup_scratch(S, ws, ws_big, ws_save, pb.n, true, save);
+  setup_scratch<M, SMEM>(S, ws, ws_big, ws_save, pb.n, true, save);
   const int b = blockIdx.y, r0 = blockIdx.x * kCh;
   const int nr = min(kCh, pb.R - r0);
   const size_t chain0 = (size_t)b * pb.R + r0;
@@ -486,8 +487,27 @@ int check_problem(const magi_problem_t* pb) {
   return MAGI_OK;
 }
 
+// ---- fast path dispatch (posterior_fast.cuh) ----
+template <class M>
+constexpr bool fast_model() { return M::D <= kFastMaxD; }
+template <class M>
+bool use_fast(int n) { return fast_model<M>() && magi_pad8(n) <= kFastMaxNp; }
+
+int sm_count() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms > 0 ? sms : 148;
+}
+// persistent grid: one CTA per SM (or fewer when there are fewer items)
+int fast_grid(const magi_problem_t* pb) {
+  const long items = (long)pb->B * ((pb->R + kCh - 1) / kCh);
+  const int sms = sm_count();
+  return (int)(items < sms ? items : sms);
+}
+
 template <class M>
 size_t workspace_bytes_t(const magi_problem_t* pb) {
+  if (use_fast<M>(pb->n)) return (size_t)sm_count() * 3 * fast_slot_elems<M>(magi_pad8(pb->n)) * sizeof(double);
   const Placement<M> p = placement<M>(pb->n, true, true);
   const size_t ncta = (size_t)pb->B * ((pb->R + kCh - 1) / kCh);
   return ncta * (p.ws_big_elems + p.ws_save_elems) * sizeof(double);
@@ -497,14 +517,28 @@ template <class M>
 int launch_logpost(const magi_problem_t* pb, const double* X, const double* sig_pre, const double* th_pre,
                    const double* beta_temp, double* lp, double* gX, double* gsig, double* gth, void* ws,
                    size_t ws_bytes, cudaStream_t st) {
+  if constexpr (fast_model<M>()) {
+    if (use_fast<M>(pb->n)) {
+      const int np = magi_pad8(pb->n);
+      const size_t smem = FastScratch<M, 0>::elems(np) * sizeof(double);
+      auto kern = np == kFastMaxNp ? logpost_grad_fast_kernel<M, kFastMaxNp> : logpost_grad_fast_kernel<M, 0>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return magi_cuda_status(e);
+      kern<<<fast_grid(pb), 32 * (np / 8), smem, st>>>(*pb, X, sig_pre, th_pre, beta_temp, lp, gX, gsig, gth);
+      return magi_cuda_status(cudaGetLastError());
+    }
+  }
   const Placement<M> p = placement<M>(pb->n, false, false);
   const dim3 grid((pb->R + kCh - 1) / kCh, pb->B);
   if (p.ws_big_elems && (!ws || ws_bytes < (size_t)grid.x * grid.y * p.ws_big_elems * sizeof(double))) return -10;
-  cudaError_t e = cudaFuncSetAttribute(logpost_grad_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)p.smem_bytes);
+  auto kern = p.big_in_smem ? logpost_grad_kernel<M, true> : logpost_grad_kernel<M, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
   if (e != cudaSuccess) return magi_cuda_status(e);
-  logpost_grad_kernel<M><<<grid, threads_for(pb->n), p.smem_bytes, st>>>(*pb, X, sig_pre, th_pre, beta_temp, lp, gX, gsig,
-                                                               gth, static_cast<double*>(ws), p.ws_big_elems);
+#ifdef MAGI_CARVEOUT
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, MAGI_CARVEOUT);
+#endif
+  kern<<<grid, threads_for(pb->n), p.smem_bytes, st>>>(*pb, X, sig_pre, th_pre, beta_temp, lp, gX, gsig, gth,
+                                                       static_cast<double*>(ws), p.ws_big_elems);
   return magi_cuda_status(cudaGetLastError());
 }
 
@@ -512,15 +546,28 @@ template <class M>
 int launch_leapfrog(const magi_problem_t* pb, double* X, double* sig_pre, double* th_pre, double* pX,
                     double* psig, double* pth, const double* eps, const double* beta_temp, int n_steps,
                     double* lp_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if constexpr (fast_model<M>()) {
+    if (use_fast<M>(pb->n)) {
+      const int np = magi_pad8(pb->n);
+      const size_t smem = FastScratch<M, 0>::elems(np) * sizeof(double);
+      const int grid = fast_grid(pb);
+      if (!ws || ws_bytes < (size_t)grid * fast_slot_elems<M>(np) * sizeof(double)) return -12;
+      auto kern = np == kFastMaxNp ? leapfrog_fast_kernel<M, kFastMaxNp> : leapfrog_fast_kernel<M, 0>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return magi_cuda_status(e);
+      kern<<<grid, 32 * (np / 8), smem, st>>>(*pb, X, sig_pre, th_pre, pX, psig, pth, eps, beta_temp, n_steps, lp_out,
+                                             static_cast<double*>(ws));
+      return magi_cuda_status(cudaGetLastError());
+    }
+  }
   const Placement<M> p = placement<M>(pb->n, true, false);
   const dim3 grid((pb->R + kCh - 1) / kCh, pb->B);
   if (p.ws_big_elems && (!ws || ws_bytes < (size_t)grid.x * grid.y * p.ws_big_elems * sizeof(double))) return -12;
-  cudaError_t e = cudaFuncSetAttribute(leapfrog_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)p.smem_bytes);
+  auto kern = p.big_in_smem ? leapfrog_kernel<M, true> : leapfrog_kernel<M, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
   if (e != cudaSuccess) return magi_cuda_status(e);
-  leapfrog_kernel<M><<<grid, threads_for(pb->n), p.smem_bytes, st>>>(*pb, X, sig_pre, th_pre, pX, psig, pth, eps, beta_temp,
-                                                           n_steps, lp_out, static_cast<double*>(ws),
-                                                           p.ws_big_elems);
+  kern<<<grid, threads_for(pb->n), p.smem_bytes, st>>>(*pb, X, sig_pre, th_pre, pX, psig, pth, eps, beta_temp, n_steps,
+                                                       lp_out, static_cast<double*>(ws), p.ws_big_elems);
   return magi_cuda_status(cudaGetLastError());
 }
 
@@ -528,15 +575,29 @@ template <class M>
 int launch_hmc(const magi_problem_t* pb, const magi_hmc_config_t* cfg, double* X, double* sig_pre,
                double* th_pre, double* eps, double* da_state, HmcOut out, void* ws, size_t ws_bytes,
                cudaStream_t st) {
+  if constexpr (fast_model<M>()) {
+    if (use_fast<M>(pb->n)) {
+      const int np = magi_pad8(pb->n);
+      const size_t smem = FastScratch<M, 0>::elems(np) * sizeof(double);
+      const int grid = fast_grid(pb);
+      if (!ws || ws_bytes < (size_t)grid * 3 * fast_slot_elems<M>(np) * sizeof(double)) return -15;
+      auto kern = np == kFastMaxNp ? hmc_fast_kernel<M, kFastMaxNp> : hmc_fast_kernel<M, 0>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return magi_cuda_status(e);
+      kern<<<grid, 32 * (np / 8), smem, st>>>(*pb, *cfg, X, sig_pre, th_pre, eps, da_state, out,
+                                             static_cast<double*>(ws));
+      return magi_cuda_status(cudaGetLastError());
+    }
+  }
   const Placement<M> p = placement<M>(pb->n, true, true);
   const dim3 grid((pb->R + kCh - 1) / kCh, pb->B);
   const size_t need = (size_t)grid.x * grid.y * (p.ws_big_elems + p.ws_save_elems) * sizeof(double);
   if (!ws || ws_bytes < need) return -15;
-  cudaError_t e =
-      cudaFuncSetAttribute(hmc_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
+  auto kern = p.big_in_smem ? hmc_kernel<M, true> : hmc_kernel<M, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_bytes);
   if (e != cudaSuccess) return magi_cuda_status(e);
-  hmc_kernel<M><<<grid, threads_for(pb->n), p.smem_bytes, st>>>(*pb, *cfg, X, sig_pre, th_pre, eps, da_state, out,
-                                                      static_cast<double*>(ws), p.ws_big_elems, p.ws_save_elems);
+  kern<<<grid, threads_for(pb->n), p.smem_bytes, st>>>(*pb, *cfg, X, sig_pre, th_pre, eps, da_state, out,
+                                                       static_cast<double*>(ws), p.ws_big_elems, p.ws_save_elems);
   return magi_cuda_status(cudaGetLastError());
 }
 
