@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MAGI_B200_ABI_VERSION 1
+#define MAGI_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MAGI_API __attribute__((visibility("default")))
@@ -90,8 +90,9 @@ MAGI_API int magi_b200_factor_derive(const double* C, const double* Cp, const do
 
 /* ---- (3a) capture the constants of the log-posterior ---------------------------------------------
  * Replaces the closure capture at magi_v2.py:294-296: re-lays C^-1, m, K^-1 [B, D, n, n] into the
- * sampler's device format (per (b,d): sym(C^-1) | m | sym(K^-1), rows padded to a multiple of 8
- * doubles, sym(A) = (A + A^T)/2 so that value AND gradient of x^T A x are those of the possibly
+ * sampler's device format (opaque; per (b,d): sym(C^-1) | m | sym(K^-1), each padded with zeros to
+ * np = 8*ceil(n/8) and stored as 8x8 tiles so that a warp streams 8 matrix rows as one contiguous
+ * run; sym(A) = (A + A^T)/2 so that value AND gradient of x^T A x are those of the possibly
  * non-symmetric A the reference holds).  Done once per fit; `packed` needs
  * magi_b200_packed_bytes(B, D, n) bytes.                                                           */
 MAGI_API size_t magi_b200_packed_bytes(int B, int D, int n);
@@ -110,6 +111,8 @@ typedef struct {
   const double* N_ds;    /* [B, D]   non-NaN raw observation counts (:53) */
   const double* beta;    /* [B]      D*n / sum(N_ds) (:89) */
   const double* LB;      /* [B, D]   sigma_sqs_LB (:299-300) */
+  int band;              /* bandsize the packed matrices were banded with (magi_v2.py:271-274): entries with
+                            |i-j| > band are exactly zero and their tiles are not read; < 0 = dense */
 } magi_problem_t;
 
 /* ---- (3b) log-posterior and analytic gradient ------------------------------------------------------

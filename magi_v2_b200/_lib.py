@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MAGI_B200_LIB", os.path.join(HERE, "libmagi_b200.so"))   # override: kernel experiments
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MODEL_IDS = {"seir3": 0, "seir4": 1, "sirw": 2, "lorenz96": 3}
 COV_UNIFORM_GRID = 1
 
@@ -20,7 +20,8 @@ class Problem(C.Structure):
     """magi_problem_t"""
     _fields_ = [("model_id", C.c_int), ("B", C.c_int), ("R", C.c_int), ("n", C.c_int), ("D", C.c_int),
                 ("P", C.c_int), ("packed", C.c_void_p), ("mu", C.c_void_p), ("y", C.c_void_p),
-                ("mask", C.c_void_p), ("N_ds", C.c_void_p), ("beta", C.c_void_p), ("LB", C.c_void_p)]
+                ("mask", C.c_void_p), ("N_ds", C.c_void_p), ("beta", C.c_void_p), ("LB", C.c_void_p),
+                ("band", C.c_int)]
 
 
 class HmcConfig(C.Structure):

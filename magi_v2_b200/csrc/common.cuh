@@ -14,7 +14,8 @@ static inline int magi_cuda_status(cudaError_t e) { return e == cudaSuccess ? MA
 // rows/cols of the packed matrices are padded to a multiple of 8 doubles (64 B)
 __host__ __device__ static inline int magi_pad8(int n) { return (n + 7) & ~7; }
 
-// packed layout: [B][D][3][np][np], slot 0 = sym(C^-1), 1 = m, 2 = sym(K^-1); padding is zero.
+// packed layout: [B][D][3][np/8][np/8][8][8] (8x8 tiles, row-major in the tile), slot 0 = sym(C^-1),
+// 1 = m, 2 = sym(K^-1); padding is zero.
 __host__ __device__ static inline size_t magi_packed_mat_elems(int n) {
   return (size_t)magi_pad8(n) * (size_t)magi_pad8(n);
 }

@@ -132,10 +132,15 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // 16 B at x[chain g][8s + 2c].
 constexpr int kFwd = 0, kTr = 1, kNone = -1;
 
+// Packed matrices are stored TILED: [row block rb][column step s] tiles of 8 x 8 doubles (512 B, row-major
+// inside the tile), so that one warp-wide 128-bit load of a forward stream reads one whole contiguous
+// tile (lane l <- bytes 16 l .. 16 l + 15) and a warp streams 8 rows of a matrix as one contiguous run
+// of np/8 tiles -- DRAM-page friendly.  A transposed stream reads the tiles of one block COLUMN
+// (stride np/8 tiles), two 8-byte loads per lane per tile.
 template <int TR>
 __device__ __forceinline__ const double* stream_ptr(const double* A, int np, int blk, int lane) {
-  return TR == kTr ? A + (size_t)(2 * (lane & 3)) * np + blk * 8 + (lane >> 2)
-                   : A + (size_t)(blk * 8 + (lane >> 2)) * np + 2 * (lane & 3);
+  return TR == kTr ? A + (size_t)blk * 64 + 16 * (lane & 3) + (lane >> 2)
+                   : A + (size_t)blk * (np >> 3) * 64 + 2 * lane;
 }
 
 __device__ __forceinline__ double2 ldg_f64x2(const double* p) {
@@ -165,45 +170,58 @@ __device__ __forceinline__ double ldg_f64(const double* p) {
 #endif
 }
 
-// step s of a stream (zero beyond the last step)
+// Column steps (forward) / row steps (transposed) of a block that can hold non-zeros when the matrices
+// are banded (tf.linalg.band_part, magi_v2.py:271-274): tile (blk, s) is non-zero only if
+// |s - blk| <= kb with kb = floor((band + 7) / 8).  Dense matrices: kb >= number of blocks.
+struct StepRange {
+  int lo, hi;  // steps lo .. hi-1
+};
+__device__ __forceinline__ int band_blocks(int band, int nblk) { return band < 0 ? nblk : (band + 7) >> 3; }
+__device__ __forceinline__ StepRange band_range(int blk, int nblk, int kb) {
+  return StepRange{max(0, blk - kb), min(nblk, blk + kb + 1)};
+}
+
+// step s of a stream (zero at and beyond step `hi`)
 template <int TR>
-__device__ __forceinline__ double2 load_step(const double* p, int s, int nk8, int np) {
+__device__ __forceinline__ double2 load_step(const double* p, int s, int hi, int np) {
   double2 v = make_double2(0.0, 0.0);
-  if (s < nk8) {
+  if (s < hi) {
     if (TR == kTr) {
-      v.x = ldg_f64(p + (size_t)(8 * s) * np);
-      v.y = ldg_f64(p + (size_t)(8 * s + 1) * np);
+      v.x = ldg_f64(p + (size_t)s * (np >> 3) * 64);
+      v.y = ldg_f64(p + (size_t)s * (np >> 3) * 64 + 8);
     } else {
-      v = ldg_f64x2(p + 8 * s);
+      v = ldg_f64x2(p + 64 * s);
     }
   }
   return v;
 }
 
 template <int TR>
-__device__ __forceinline__ void load_batch(double2 (&a)[kU], const double* p, int nk8, int np) {
+__device__ __forceinline__ void load_batch(double2 (&a)[kU], const double* p, StepRange r, int np) {
 #pragma unroll
-  for (int u = 0; u < kU; ++u) a[u] = load_step<TR>(p, u, nk8, np);
+  for (int u = 0; u < kU; ++u) a[u] = load_step<TR>(p, r.lo + u, r.hi, np);
 }
 
 // One 8-row (CT = kFwd) or 8-column (CT = kTr) block of a contraction with the 8 chain vectors x[8][ns]
-// (or x - xsub when SUB): a rolling register pipeline.  On entry a[u] holds step u of the current stream
-// `cp` (u < kU); every register is refilled with step s + kU as soon as step s has been consumed, so kU
-// 16-byte loads per lane stay in flight; during the last batch the refills switch to the warp's NEXT
-// task `np_` of kind NT (possibly in a later phase, behind a __syncthreads; nullptr or NT = kNone: no
-// next task), whose first kU steps are therefore already in flight when it starts.
-// Result: c0, c1 = y[chain 2c], y[chain 2c+1] at block element g (lane = 4g + c).
+// (or x - xsub when SUB) over the steps `cr`: a rolling register pipeline.  On entry a[u] holds step
+// cr.lo + u of the current stream `cp` (u < kU); every register is refilled with step s + kU as soon as
+// step s has been consumed, so kU 16-byte loads per lane stay in flight; during the last batch the
+// refills switch to the warp's NEXT task (`nxp`, kind NT, steps `nr`; possibly in a later phase, behind
+// a __syncthreads; nullptr: no next task), whose first kU steps are therefore already in flight when
+// it starts.  Result: c0, c1 = y[chain 2c], y[chain 2c+1] at block element g (lane = 4g + c).
 template <bool SUB, int CT, int NT>
-__device__ __forceinline__ void mma_task(double2 (&a)[kU], const double* cp, const double* nxp, const double* x,
-                                         const double* xsub, int ns, int nk8, int np, double& c0, double& c1) {
+__device__ __forceinline__ void mma_task(double2 (&a)[kU], const double* cp, StepRange cr, const double* nxp,
+                                         StepRange nr, const double* x, const double* xsub, int ns, int np,
+                                         double& c0, double& c1) {
   const int lane = threadIdx.x & 31;
   const size_t bo = (size_t)(lane >> 2) * ns + 2 * (lane & 3);
   const double* bp = x + bo;
   const double* bs = SUB ? xsub + bo : nullptr;
-  const int nlast = ((nk8 - 1) / kU) * kU;  // first step of the last batch
-  double acc[4][2];
+  const int nsteps = cr.hi - cr.lo;
+  const int nlast = cr.lo + ((nsteps - 1) / kU) * kU;  // first step of the last batch
+  double acc[2][2];  // two independent accumulator pairs (even / odd k-group of a step)
 #pragma unroll
-  for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = 0.0;
+  for (int q = 0; q < 2; ++q) acc[q][0] = acc[q][1] = 0.0;
   auto consume = [&](int s, int u) {
     double2 b = *reinterpret_cast<const double2*>(bp + 8 * s);
     if (SUB) {
@@ -211,25 +229,25 @@ __device__ __forceinline__ void mma_task(double2 (&a)[kU], const double* cp, con
       b.x -= b2.x;
       b.y -= b2.y;
     }
-    dmma(acc[(2 * u) & 3][0], acc[(2 * u) & 3][1], a[u].x, b.x);
-    dmma(acc[(2 * u + 1) & 3][0], acc[(2 * u + 1) & 3][1], a[u].y, b.y);
+    dmma(acc[0][0], acc[0][1], a[u].x, b.x);
+    dmma(acc[1][0], acc[1][1], a[u].y, b.y);
   };
 #pragma unroll 1
-  for (int s0 = 0; s0 < nlast; s0 += kU) {
+  for (int s0 = cr.lo; s0 < nlast; s0 += kU) {
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       consume(s0 + u, u);
-      a[u] = load_step<CT>(cp, s0 + u + kU, nk8, np);
+      a[u] = load_step<CT>(cp, s0 + u + kU, cr.hi, np);
     }
   }
-  const int nnext = (NT != kNone && nxp != nullptr) ? nk8 : 0;
+  const int nhi = nxp != nullptr ? nr.hi : 0;
 #pragma unroll
   for (int u = 0; u < kU; ++u) {
-    if (nlast + u < nk8) consume(nlast + u, u);
-    a[u] = load_step<(NT == kNone ? kFwd : NT)>(nxp, u, nnext, np);
+    if (nlast + u < cr.hi) consume(nlast + u, u);
+    a[u] = load_step<NT>(nxp, nr.lo + u, nhi, np);
   }
-  c0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
-  c1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+  c0 = acc[0][0] + acc[1][0];
+  c1 = acc[0][1] + acc[1][1];
 }
 
 // Per-chain transforms of the small state parts (magi_v2.py:318-319).  Threads 0..7.
@@ -256,7 +274,8 @@ __device__ __forceinline__ void chain_scalars(const Scratch<M>& S) {
 // (S.Xc centred trajectories, S.tau, S.s).  Results: S.L[8], S.GX (dL/dX), S.gtau, S.gs.
 // `mats` = packed matrices of this dataset: [D][3][np][np].  All threads must call.
 template <class M>
-__device__ void eval_logpost_grad(const Scratch<M>& S, const double* __restrict__ mats, double inv_beta) {
+__device__ void eval_logpost_grad(const Scratch<M>& S, const double* __restrict__ mats, double inv_beta,
+                                  int band) {
   constexpr int D = M::D, P = M::P, NRED = Scratch<M>::NRED;
   const int n = S.n, np = S.np, ns = S.ns;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
@@ -265,12 +284,14 @@ __device__ void eval_logpost_grad(const Scratch<M>& S, const double* __restrict_
   const size_t msz = (size_t)np * np;
   const int nblk = np >> 3;  // 8-row blocks = 8-column steps
   const int g = lane >> 2, c2 = 2 * (lane & 3);
+  const int kb = band_blocks(band, nblk);
+  auto rng = [&](int blk) { return band_range(blk, nblk, kb); };
 
   chain_scalars(S);
   // first matrix batch of this warp goes in flight before anything else
   double2 a[kU];
   const bool active = warp < nblk;
-  if (active) load_batch<kFwd>(a, stream_ptr<kFwd>(mats, np, warp, lane), nblk, np);
+  if (active) load_batch<kFwd>(a, stream_ptr<kFwd>(mats, np, warp, lane), rng(warp), np);
   __syncthreads();
 
   double th[P];
@@ -303,7 +324,8 @@ __device__ void eval_logpost_grad(const Scratch<M>& S, const double* __restrict_
     for (int blk = warp; blk < nblk; blk += nw) {
       double c0, c1;
       const double* sm = stream_ptr<kFwd>(Mm, np, blk, lane);
-      mma_task<false, kFwd, kFwd>(a, stream_ptr<kFwd>(SC, np, blk, lane), sm, xc, nullptr, ns, nblk, np, c0, c1);
+      mma_task<false, kFwd, kFwd>(a, stream_ptr<kFwd>(SC, np, blk, lane), rng(blk), sm, rng(blk), xc, nullptr, ns, np,
+                                  c0, c1);
       gx[(size_t)c2 * ns + blk * 8 + g] = 2.0 * c0;
       gx[(size_t)(c2 + 1) * ns + blk * 8 + g] = 2.0 * c1;
       t1a = fma(xc[(size_t)c2 * ns + blk * 8 + g], c0, t1a);  // xc . S_C xc for chains 2c, 2c+1
@@ -311,7 +333,7 @@ __device__ void eval_logpost_grad(const Scratch<M>& S, const double* __restrict_
       const bool more = blk + nw < nblk;
       const double* nx = more ? stream_ptr<kFwd>(SC, np, blk + nw, lane)
                               : (chain_next ? stream_ptr<kFwd>(SK, np, warp, lane) : nullptr);
-      mma_task<false, kFwd, kFwd>(a, sm, nx, xc, nullptr, ns, nblk, np, c0, c1);
+      mma_task<false, kFwd, kFwd>(a, sm, rng(blk), nx, rng(more ? blk + nw : warp), xc, nullptr, ns, np, c0, c1);
       wa[(size_t)c2 * ns + blk * 8 + g] = c0;
       wa[(size_t)(c2 + 1) * ns + blk * 8 + g] = c1;
     }
@@ -329,9 +351,11 @@ __device__ void eval_logpost_grad(const Scratch<M>& S, const double* __restrict_
       double c0, c1;
       const double* cur = stream_ptr<kFwd>(SK, np, blk, lane);
       if (blk + nw < nblk)
-        mma_task<true, kFwd, kFwd>(a, cur, stream_ptr<kFwd>(SK, np, blk + nw, lane), fg, wa, ns, nblk, np, c0, c1);
+        mma_task<true, kFwd, kFwd>(a, cur, rng(blk), stream_ptr<kFwd>(SK, np, blk + nw, lane), rng(blk + nw), fg, wa,
+                                   ns, np, c0, c1);
       else
-        mma_task<true, kFwd, kTr>(a, cur, stream_ptr<kTr>(Mm, np, warp, lane), fg, wa, ns, nblk, np, c0, c1);
+        mma_task<true, kFwd, kTr>(a, cur, rng(blk), stream_ptr<kTr>(Mm, np, warp, lane), rng(warp), fg, wa, ns, np,
+                                  c0, c1);
       S.Wb[(size_t)c2 * ns + blk * 8 + g] = 2.0 * c0;
       S.Wb[(size_t)(c2 + 1) * ns + blk * 8 + g] = 2.0 * c1;
     }
@@ -341,12 +365,13 @@ __device__ void eval_logpost_grad(const Scratch<M>& S, const double* __restrict_
       double c0, c1;
       const double* cur = stream_ptr<kTr>(Mm, np, blk, lane);
       if (blk + nw < nblk)
-        mma_task<false, kTr, kTr>(a, cur, stream_ptr<kTr>(Mm, np, blk + nw, lane), S.Wb, nullptr, ns, nblk, np, c0, c1);
+        mma_task<false, kTr, kTr>(a, cur, rng(blk), stream_ptr<kTr>(Mm, np, blk + nw, lane), rng(blk + nw), S.Wb,
+                                  nullptr, ns, np, c0, c1);
       else
-        mma_task<false, kTr, kFwd>(a, cur,
+        mma_task<false, kTr, kFwd>(a, cur, rng(blk),
                                    d + 1 < D ? stream_ptr<kFwd>(mats + (size_t)(3 * (d + 1)) * msz, np, warp, lane)
                                              : nullptr,
-                                   S.Wb, nullptr, ns, nblk, np, c0, c1);
+                                   rng(warp), S.Wb, nullptr, ns, np, c0, c1);
       gx[(size_t)c2 * ns + blk * 8 + g] -= c0;
       gx[(size_t)(c2 + 1) * ns + blk * 8 + g] -= c1;
     }

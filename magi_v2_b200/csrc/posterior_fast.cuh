@@ -18,6 +18,13 @@
 #pragma once
 #include "posterior_core.cuh"
 
+// experiment knobs (tools/build_variant.sh only; never defined in the product build)
+#ifdef MAGI_EXP_NOSYNC
+#define MAGI_PHASE_SYNC() ((void)0)
+#else
+#define MAGI_PHASE_SYNC() __syncthreads()
+#endif
+
 constexpr int kFastMaxNp = 168;
 constexpr int kFastMaxD = 4;
 
@@ -90,8 +97,8 @@ __device__ __forceinline__ double fold_g(double v) {
 // j >= n), and a[] holds the first steps of `next_mats` (if not null).  All threads must call.
 template <class M, int NP>
 __device__ void fast_eval(const FastScratch<M, NP>& S, const double* __restrict__ mats,
-                          const double* __restrict__ next_mats, double inv_beta, double (&gxr)[M::D][2],
-                          double2 (&a)[kU]) {
+                          const double* __restrict__ next_mats, double inv_beta, int band,
+                          double (&gxr)[M::D][2], double2 (&a)[kU]) {
   constexpr int D = M::D, P = M::P, NRED = FastScratch<M, NP>::NRED;
   const int n = S.n, np = S.np(), ns = S.ns();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = S.nblk();
@@ -99,6 +106,7 @@ __device__ void fast_eval(const FastScratch<M, NP>& S, const double* __restrict_
   const int j = warp * 8 + g;
   const size_t msz = (size_t)np * np;
   const int nblk = S.nblk();
+  const StepRange rg = band_range(warp, nblk, band_blocks(band, nblk));  // same for every task of this warp
   const bool valid = j < n;
   const size_t o0 = (size_t)c2 * ns + j, o1 = o0 + ns;  // own elements inside one [8][ns] array
 
@@ -142,17 +150,17 @@ __device__ void fast_eval(const FastScratch<M, NP>& S, const double* __restrict_
     const double* xc = S.Xc() + S.vix(d, 0, 0);
     double c0, c1;
     const double* sm = stream_ptr<kFwd>(Mm, np, warp, lane);
-    mma_task<false, kFwd, kFwd>(a, stream_ptr<kFwd>(SC, np, warp, lane), sm, xc, nullptr, ns, nblk, np, c0, c1);
+    mma_task<false, kFwd, kFwd>(a, stream_ptr<kFwd>(SC, np, warp, lane), rg, sm, rg, xc, nullptr, ns, np, c0, c1);
     gxr[d][0] = 2.0 * c0;
     gxr[d][1] = 2.0 * c1;
     t1[0] = fma(xc[o0], c0, t1[0]);
     t1[1] = fma(xc[o1], c1, t1[1]);
-    mma_task<false, kFwd, kFwd>(a, sm, stream_ptr<kFwd>(SK, np, warp, lane), xc, nullptr, ns, nblk, np, c0, c1);
+    mma_task<false, kFwd, kFwd>(a, sm, rg, stream_ptr<kFwd>(SK, np, warp, lane), rg, xc, nullptr, ns, np, c0, c1);
     S.Wa()[o0] = c0;
     S.Wa()[o1] = c1;
   };
   pass_a(0);
-  __syncthreads();
+  MAGI_PHASE_SYNC();
 #pragma unroll
   for (int d = 0; d < D; ++d) {
     const double* Mm = mats + (size_t)(3 * d + 1) * msz;
@@ -161,8 +169,8 @@ __device__ void fast_eval(const FastScratch<M, NP>& S, const double* __restrict_
     double g0, g1;
     {  // B(d): g = 2 S_K (f - w) -> Wb ; t2 += (f - w) . S_K (f - w)
       double c0, c1;
-      mma_task<true, kFwd, kTr>(a, stream_ptr<kFwd>(SK, np, warp, lane), stream_ptr<kTr>(Mm, np, warp, lane), fg,
-                                S.Wa(), ns, nblk, np, c0, c1);
+      mma_task<true, kFwd, kTr>(a, stream_ptr<kFwd>(SK, np, warp, lane), rg, stream_ptr<kTr>(Mm, np, warp, lane), rg,
+                                fg, S.Wa(), ns, np, c0, c1);
       g0 = 2.0 * c0;
       g1 = 2.0 * c1;
       S.Wb()[o0] = g0;
@@ -170,13 +178,17 @@ __device__ void fast_eval(const FastScratch<M, NP>& S, const double* __restrict_
       t2[0] = fma(fg[o0] - S.Wa()[o0], c0, t2[0]);
       t2[1] = fma(fg[o1] - S.Wa()[o1], c1, t2[1]);
     }
-    __syncthreads();
+    MAGI_PHASE_SYNC();
     {  // C(d): gxr -= m^T g (second read of m: L2) ; FG_d <- g ; A(d+1)
       double c0, c1;
       const bool last = d + 1 == D;
       const double* nm = last ? next_mats : mats + (size_t)(3 * (d + 1)) * msz;
-      mma_task<false, kTr, kFwd>(a, stream_ptr<kTr>(Mm, np, warp, lane),
-                                 nm ? stream_ptr<kFwd>(nm, np, warp, lane) : nullptr, S.Wb(), nullptr, ns, nblk, np,
+#ifdef MAGI_EXP_SKIPC
+      mma_task<false, kFwd, kFwd>(a, stream_ptr<kFwd>(SK, np, warp, lane), rg,
+#else
+      mma_task<false, kTr, kFwd>(a, stream_ptr<kTr>(Mm, np, warp, lane), rg,
+#endif
+                                 nm ? stream_ptr<kFwd>(nm, np, warp, lane) : nullptr, rg, S.Wb(), nullptr, ns, np,
                                  c0, c1);
       gxr[d][0] -= c0;
       gxr[d][1] -= c1;
@@ -184,7 +196,7 @@ __device__ void fast_eval(const FastScratch<M, NP>& S, const double* __restrict_
       fg[o1] = g1;
       if (!last) pass_a(d + 1);
     }
-    __syncthreads();
+    MAGI_PHASE_SYNC();
   }
 
   // pointwise epilogue at the own elements: ODE Jacobian terms, likelihood, assemble the gradient

@@ -10,7 +10,7 @@ namespace {
 constexpr size_t kMaxSmem = 227 * 1024;
 
 // ------------------------------------------------------------------------------------------------
-// pack: [B,D,n,n] x3 (reference layout) -> [B][D][3][np][np] with symmetrised quadratic forms
+// pack: [B,D,n,n] x3 (reference layout) -> [B][D][3][np/8][np/8][8][8] tiles with symmetrised quadratic forms
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_kernel(const double* __restrict__ Cinv, const double* __restrict__ m,
                             const double* __restrict__ Kinv, int n, int np, double* __restrict__ out) {
@@ -19,7 +19,8 @@ __global__ void pack_kernel(const double* __restrict__ Cinv, const double* __res
   const double* c = Cinv + bd * (size_t)n * n;
   const double* mm = m + bd * (size_t)n * n;
   const double* k = Kinv + bd * (size_t)n * n;
-  double* o = out + bd * 3 * (size_t)np * np + (size_t)i * np;
+  double* o = out + bd * 3 * (size_t)np * np;
+  const int nblk = np >> 3;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < np; j += gridDim.x * blockDim.x) {
     double sc = 0.0, mv = 0.0, sk = 0.0;
     if (i < n && j < n) {
@@ -27,9 +28,10 @@ __global__ void pack_kernel(const double* __restrict__ Cinv, const double* __res
       mv = mm[(size_t)i * n + j];
       sk = 0.5 * (k[(size_t)i * n + j] + k[(size_t)j * n + i]);
     }
-    o[j] = sc;
-    o[(size_t)np * np + j] = mv;
-    o[2 * (size_t)np * np + j] = sk;
+    const size_t t = ((size_t)(i >> 3) * nblk + (j >> 3)) * 64 + (i & 7) * 8 + (j & 7);  // tiled offset
+    o[t] = sc;
+    o[(size_t)np * np + t] = mv;
+    o[2 * (size_t)np * np + t] = sk;
   }
 }
 
@@ -104,7 +106,7 @@ logpost_grad_kernel(magi_problem_t pb, const double* __restrict__ X, const doubl
   load_state(S, X, sig_pre, th_pre, chain0, nr);
   __syncthreads();
   const double* mats = static_cast<const double*>(pb.packed) + (size_t)b * D * 3 * np * np;
-  eval_logpost_grad(S, mats, 1.0 / pb.beta[b]);
+  eval_logpost_grad(S, mats, 1.0 / pb.beta[b], pb.band);
 
   // scale by the temperature and store in the reference layout
   const int per = n * D;
@@ -177,14 +179,14 @@ __device__ __forceinline__ void drift(const Scratch<M>& S, const double* epsv) {
 // TFP SimpleLeapfrogIntegrator: per step  p += eps/2 g;  z += eps p;  g = grad(z);  p += eps/2 g.
 // Requires the gradient at the current z in scratch on entry; leaves the gradient at the end point.
 template <class M>
-__device__ void leapfrog_steps(const Scratch<M>& S, const double* mats, double inv_beta, const double* epsv,
-                               const double* btv, int n_steps) {
+__device__ void leapfrog_steps(const Scratch<M>& S, const double* mats, double inv_beta, int band,
+                               const double* epsv, const double* btv, int n_steps) {
   for (int st = 0; st < n_steps; ++st) {
     kick(S, epsv, btv, 0.5);
     __syncthreads();
     drift(S, epsv);
     __syncthreads();
-    eval_logpost_grad(S, mats, inv_beta);
+    eval_logpost_grad(S, mats, inv_beta, band);
     kick(S, epsv, btv, 0.5);
     __syncthreads();
   }
@@ -261,8 +263,8 @@ leapfrog_kernel(magi_problem_t pb, double* X, double* sig_pre, double* th_pre, d
   __syncthreads();
   const double* mats = static_cast<const double*>(pb.packed) + (size_t)b * D * 3 * np * np;
   const double inv_beta = 1.0 / pb.beta[b];
-  eval_logpost_grad(S, mats, inv_beta);
-  leapfrog_steps(S, mats, inv_beta, epsv, btv, n_steps);
+  eval_logpost_grad(S, mats, inv_beta, pb.band);
+  leapfrog_steps(S, mats, inv_beta, pb.band, epsv, btv, n_steps);
 
   for (int e = tid; e < nr * per; e += blockDim.x) {
     const int r = e / per, rem = e - r * per;
@@ -331,7 +333,7 @@ hmc_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig_pre,
   __syncthreads();
   const double* mats = static_cast<const double*>(pb.packed) + (size_t)b * D * 3 * np * np;
   const double inv_beta = 1.0 / pb.beta[b];
-  eval_logpost_grad(S, mats, inv_beta);
+  eval_logpost_grad(S, mats, inv_beta, pb.band);
 
   const int nstate = n * D + D + P;
   const int npairs = (nstate + 1) >> 1;
@@ -381,7 +383,7 @@ hmc_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig_pre,
     if (tid < kCh) h0[tid] = -bt * S.L[tid] + ke[tid];
     __syncthreads();
 
-    leapfrog_steps(S, mats, inv_beta, epsv, btv, cfg.n_leapfrog);
+    leapfrog_steps(S, mats, inv_beta, pb.band, epsv, btv, cfg.n_leapfrog);
 
     kinetic(S, ke);
     if (tid < kCh) {

@@ -49,14 +49,18 @@ logpost_grad_fast_kernel(magi_problem_t pb, const double* __restrict__ X, const 
   size_t chain0;
   double2 a[kU];
   if (fast_item<M>(pb, blockIdx.x, b, nr, chain0))
-    load_batch<kFwd>(a, stream_ptr<kFwd>(fast_mats<M>(pb, b, np), np, warp, lane), np >> 3, np);
+    load_batch<kFwd>(a, stream_ptr<kFwd>(fast_mats<M>(pb, b, np), np, warp, lane),
+                     band_range(warp, np >> 3, band_blocks(pb.band, np >> 3)), np);
   for (int item = blockIdx.x; fast_item<M>(pb, item, b, nr, chain0); item += gridDim.x) {
+#ifdef MAGI_EXP_SKIPLOAD
+    if (item == (int)blockIdx.x)
+#endif
     fast_load_item(S, pb, b, X, sig_pre, th_pre, chain0, nr);
     int bn, nrn;
     size_t c0n;
     const double* next_mats = fast_item<M>(pb, item + gridDim.x, bn, nrn, c0n) ? fast_mats<M>(pb, bn, np) : nullptr;
     double gxr[D][2];
-    fast_eval(S, fast_mats<M>(pb, b, np), next_mats, 1.0 / pb.beta[b], gxr, a);
+    fast_eval(S, fast_mats<M>(pb, b, np), next_mats, 1.0 / pb.beta[b], pb.band, gxr, a);
     // scale by the temperature and store in the reference layout X[n][D]
     if (j < n) {
 #pragma unroll
@@ -131,13 +135,13 @@ __device__ __forceinline__ void fast_kick_drift(const FastScratch<M, NP>& S, dou
 // should be in flight when the last evaluation ends (the same dataset again, the next item, or null).
 template <class M, int NP>
 __device__ void fast_leapfrog_steps(const FastScratch<M, NP>& S, double* PX, double (&gxr)[M::D][2], double2 (&a)[kU],
-                                    const double* mats, const double* next_mats, double inv_beta,
+                                    const double* mats, const double* next_mats, double inv_beta, int band,
                                     const double* epsv, const double* btv, int n_steps) {
   if (n_steps <= 0) return;
   fast_kick_drift(S, PX, gxr, epsv, btv, 0.5, true);
   for (int st = 0; st < n_steps; ++st) {
     const bool last = st + 1 == n_steps;
-    fast_eval(S, mats, last ? next_mats : mats, inv_beta, gxr, a);  // starts with a __syncthreads-protected phase
+    fast_eval(S, mats, last ? next_mats : mats, inv_beta, band, gxr, a);  // starts with a __syncthreads-protected phase
     fast_kick_drift(S, PX, gxr, epsv, btv, last ? 0.5 : 1.0, !last);
   }
   __syncthreads();
@@ -197,7 +201,8 @@ leapfrog_fast_kernel(magi_problem_t pb, double* X, double* sig_pre, double* th_p
   size_t chain0;
   double2 a[kU];
   if (fast_item<M>(pb, blockIdx.x, b, nr, chain0))
-    load_batch<kFwd>(a, stream_ptr<kFwd>(fast_mats<M>(pb, b, np), np, warp, lane), nblk, np);
+    load_batch<kFwd>(a, stream_ptr<kFwd>(fast_mats<M>(pb, b, np), np, warp, lane),
+                     band_range(warp, nblk, band_blocks(pb.band, nblk)), np);
   for (int item = blockIdx.x; fast_item<M>(pb, item, b, nr, chain0); item += gridDim.x) {
     fast_load_item(S, pb, b, X, sig_pre, th_pre, chain0, nr);
     // momenta into own-element order
@@ -226,8 +231,8 @@ leapfrog_fast_kernel(magi_problem_t pb, double* X, double* sig_pre, double* th_p
     const double* next_mats = fast_item<M>(pb, item + gridDim.x, bn, nrn, c0n) ? fast_mats<M>(pb, bn, np) : nullptr;
     const double inv_beta = 1.0 / pb.beta[b];
     double gxr[D][2];
-    fast_eval(S, mats, n_steps > 0 ? mats : next_mats, inv_beta, gxr, a);
-    fast_leapfrog_steps(S, PX, gxr, a, mats, next_mats, inv_beta, epsv, btv, n_steps);
+    fast_eval(S, mats, n_steps > 0 ? mats : next_mats, inv_beta, pb.band, gxr, a);
+    fast_leapfrog_steps(S, PX, gxr, a, mats, next_mats, inv_beta, pb.band, epsv, btv, n_steps);
 
     if (j < n) {
 #pragma unroll
@@ -293,7 +298,8 @@ hmc_fast_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig
   size_t chain0;
   double2 a[kU];
   if (fast_item<M>(pb, blockIdx.x, b, nr, chain0))
-    load_batch<kFwd>(a, stream_ptr<kFwd>(fast_mats<M>(pb, b, np), np, warp, lane), nblk, np);
+    load_batch<kFwd>(a, stream_ptr<kFwd>(fast_mats<M>(pb, b, np), np, warp, lane),
+                     band_range(warp, nblk, band_blocks(pb.band, nblk)), np);
   for (int item = blockIdx.x; fast_item<M>(pb, item, b, nr, chain0); item += gridDim.x) {
     fast_load_item(S, pb, b, X, sig_pre, th_pre, chain0, nr);
     if (tid < kCh) {
@@ -309,7 +315,7 @@ hmc_fast_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig
     const double* next_mats = fast_item<M>(pb, item + gridDim.x, bn, nrn, c0n) ? fast_mats<M>(pb, bn, np) : nullptr;
     const double inv_beta = 1.0 / pb.beta[b];
     double gxr[D][2];
-    fast_eval(S, mats, cfg.n_iter > 0 ? mats : next_mats, inv_beta, gxr, a);
+    fast_eval(S, mats, cfg.n_iter > 0 ? mats : next_mats, inv_beta, pb.band, gxr, a);
 
     for (int it = 0; it < cfg.n_iter; ++it) {
       const int git = cfg.iter0 + it;
@@ -381,7 +387,8 @@ hmc_fast_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig
       __syncthreads();
 
       const bool last_it = it + 1 == cfg.n_iter;
-      fast_leapfrog_steps(S, PX, gxr, a, mats, last_it ? next_mats : mats, inv_beta, epsv, btv, cfg.n_leapfrog);
+      fast_leapfrog_steps(S, PX, gxr, a, mats, last_it ? next_mats : mats, inv_beta, pb.band, epsv, btv,
+                          cfg.n_leapfrog);
 
       fast_kinetic(S, PX, ke);
       if (tid < kCh) {

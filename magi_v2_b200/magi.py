@@ -174,7 +174,7 @@ class MAGI_v2:
         prob = ops.PosteriorProblem(self.model.name, packed, mu=T(self.mu_ds[None]), y=T(y.reshape(1, n, D)),
                                     mask=T(mask.reshape(1, n, D), torch.uint8),
                                     N_ds=T(self.N_ds[None].astype(np.float64)), beta=T(np.array([self.beta])),
-                                    LB=T(sigma_sqs_LB[None]), n=n)
+                                    LB=T(sigma_sqs_LB[None]), n=n, band=self.BANDSIZE)
         rng = np.random.default_rng(seed)
         X0 = np.repeat(self.Xhat_init[None, None], R, axis=1)
         if init_jitter > 0.0:

@@ -122,7 +122,7 @@ class PosteriorProblem:
     ``unnormalized_log_prob`` closes over, magi_v2.py:294-300) + the ctypes view of them."""
 
     def __init__(self, model: str, packed: Tensor, mu: Tensor, y: Tensor, mask: Tensor, N_ds: Tensor,
-                 beta: Tensor, LB: Tensor, n: int):
+                 beta: Tensor, LB: Tensor, n: int, band: Optional[int] = None):
         self.model = model
         self.model_id = _lib.MODEL_IDS[model]
         D_, P_ = C.c_int(), C.c_int()
@@ -137,6 +137,9 @@ class PosteriorProblem:
             raise RuntimeError("magi_b200: packed buffer has the wrong size for (B, D, n)")
         self.packed, self.mu, self.y, self.mask, self.N_ds, self.beta, self.LB = packed, mu, y, mask, N_ds, beta, LB
         self.device = mu.device
+        # bandsize the matrices were banded with (None = dense): lets the kernels skip all-zero tiles.
+        # The caller vouches for it -- entries outside the band are never read.
+        self.band = -1 if band is None else int(band)
         self._ws = {}
         self._host = None
 
@@ -149,7 +152,7 @@ class PosteriorProblem:
                        self.packed.data_ptr() + b0 * D * 3 * npad * npad * 8,
                        self.mu.data_ptr() + b0 * D * 8, self.y.data_ptr() + b0 * n * D * 8,
                        self.mask.data_ptr() + b0 * n * D, self.N_ds.data_ptr() + b0 * D * 8,
-                       self.beta.data_ptr() + b0 * 8, self.LB.data_ptr() + b0 * D * 8)
+                       self.beta.data_ptr() + b0 * 8, self.LB.data_ptr() + b0 * D * 8, self.band)
 
     def workspace(self, R: int, slot: int = 0, n_datasets: Optional[int] = None) -> Tuple[Optional[Tensor], int]:
         """Caller-owned scratch of the sampler kernels; one buffer per concurrent stream (`slot`)."""
@@ -294,12 +297,12 @@ class PosteriorProblem:
 # ------------------------------------------------------------------------------------------------
 @torch.library.custom_op("magi_b200::logpost_grad", mutates_args=(), device_types="cuda")
 def logpost_grad(model_id: int, X: Tensor, sig_pre: Tensor, th_pre: Tensor, beta_temp: Tensor, packed: Tensor,
-                 mu: Tensor, y: Tensor, mask: Tensor, N_ds: Tensor, beta: Tensor, LB: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+                 mu: Tensor, y: Tensor, mask: Tensor, N_ds: Tensor, beta: Tensor, LB: Tensor, band: int = -1) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     name = {v: k for k, v in _lib.MODEL_IDS.items()}[model_id]
-    prob = PosteriorProblem(name, packed, mu, y, mask, N_ds, beta, LB, X.shape[2])
+    prob = PosteriorProblem(name, packed, mu, y, mask, N_ds, beta, LB, X.shape[2], None if band < 0 else band)
     return prob.logpost_grad(X, sig_pre, th_pre, beta_temp)
 
 
 @logpost_grad.register_fake
-def _(model_id, X, sig_pre, th_pre, beta_temp, packed, mu, y, mask, N_ds, beta, LB):
+def _(model_id, X, sig_pre, th_pre, beta_temp, packed, mu, y, mask, N_ds, beta, LB, band=-1):
     return X.new_empty(X.shape[:2]), torch.empty_like(X), torch.empty_like(sig_pre), torch.empty_like(th_pre)

@@ -108,7 +108,7 @@ def device_problem(model: str, I, phi1, phi2, y, mask, N_ds, beta, mu, LB, bands
         del C, Cp, Cpp, Cinv, m, Kinv
     info = torch.cat(infos)
     prob = ops.PosteriorProblem(model, packed, mu=T(mu), y=T(y), mask=T(mask, torch.uint8), N_ds=T(N_ds),
-                                beta=T(beta), LB=T(LB), n=n)
+                                beta=T(beta), LB=T(LB), n=n, band=bandsize)
     return prob, info
 
 

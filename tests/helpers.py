@@ -59,10 +59,25 @@ def random_state(c, model_name, rng, R, jitter=0.02):
     return X, s, tau
 
 
-def device_problem(consts, model_name, device):
-    """List of oracle PosteriorConstants (same n, model) -> magi_v2_b200.ops.PosteriorProblem."""
+def matrix_bandwidth(consts):
+    """Largest |i-j| holding a non-zero in any of C^-1, m, K^-1 of the given constants (the bandsize the
+    reference's band_part left, magi_v2.py:271-274), or None when the matrices are dense."""
+    bw = 0
+    n = consts[0].n
+    for c in consts:
+        for A in (c.C_d_invs, c.m_ds, c.K_d_invs):
+            i, j = np.nonzero(np.abs(A).sum(axis=0))
+            bw = max(bw, int(np.abs(i - j).max()))
+    return None if bw >= n - 1 else bw
+
+
+def device_problem(consts, model_name, device, band="auto"):
+    """List of oracle PosteriorConstants (same n, model) -> magi_v2_b200.ops.PosteriorProblem.
+    band="auto": tell the kernels the true bandwidth of the matrices; None: treat them as dense."""
     import torch
     from magi_v2_b200 import ops
+    if band == "auto":
+        band = matrix_bandwidth(consts)
 
     T = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=device)
     Cinv = T(np.stack([c.C_d_invs for c in consts]))
@@ -76,7 +91,7 @@ def device_problem(consts, model_name, device):
         y=T(np.stack(ys)), mask=T(np.stack(masks), torch.uint8),
         N_ds=T(np.stack([c.N_ds.astype(np.float64) for c in consts])),
         beta=T(np.array([c.beta for c in consts])),
-        LB=T(np.stack([c.sigma_sqs_LB for c in consts])), n=consts[0].n)
+        LB=T(np.stack([c.sigma_sqs_LB for c in consts])), n=consts[0].n, band=band)
     return prob
 
 

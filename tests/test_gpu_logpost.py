@@ -92,3 +92,22 @@ def test_linearity_in_temperature_and_chain_independence(cuda_device):
     p = _run(prob, X[None, perm], s[None, perm], tau[None, perm], np.full((1, 8), 1.0), cuda_device)
     for u, v in zip(a, p):
         assert np.array_equal(u[0][perm], v[0])
+
+
+@pytest.mark.parametrize("model", ["seir4", "lorenz96"])
+def test_band_skipping_equals_dense(model, cuda_device):
+    """Telling the kernels the bandsize (zero tiles are then not read) must not change the result:
+    same banded matrices evaluated as banded and as dense (fast path and general path)."""
+    rng = np.random.default_rng(21)
+    c = synth_constants(model, seed=8, N=41, band=12)          # n = 81: 11 row blocks, band 12 -> kb = 2
+    X, s, tau = random_state(c, model, rng, 8)
+    bt = np.full((1, 8), 0.8)
+    res = []
+    for band in ("auto", None):
+        prob = device_problem([c], model, cuda_device, band=band)
+        assert prob.band == (12 if band == "auto" else -1)
+        res.append(_run(prob, X[None], s[None], tau[None], bt, cuda_device))
+    for u, v in zip(*res):
+        assert relerr(u, v) <= 1e-13
+    o = mo.log_posterior_and_grad_autograd(X[3], s[3], tau[3], 0.8, c)
+    assert abs(res[0][0][0, 3] - o[0]) <= TOL * abs(o[0]) and relerr(res[0][1][0, 3], o[1]) <= TOL
