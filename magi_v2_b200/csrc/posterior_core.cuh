@@ -196,55 +196,55 @@ __device__ __forceinline__ double2 load_step(const double* p, int s, int hi, int
   return v;
 }
 
-template <int TR>
-__device__ __forceinline__ void load_batch(double2 (&a)[kU], const double* p, StepRange r, int np) {
+template <int TR, int U>
+__device__ __forceinline__ void load_batch(double2 (&a)[U], const double* p, StepRange r, int np) {
 #pragma unroll
-  for (int u = 0; u < kU; ++u) a[u] = load_step<TR>(p, r.lo + u, r.hi, np);
+  for (int u = 0; u < U; ++u) a[u] = load_step<TR>(p, r.lo + u, r.hi, np);
 }
 
 // One 8-row (CT = kFwd) or 8-column (CT = kTr) block of a contraction with the 8 chain vectors x[8][ns]
 // (or x - xsub when SUB) over the steps `cr`: a rolling register pipeline.  On entry a[u] holds step
-// cr.lo + u of the current stream `cp` (u < kU); every register is refilled with step s + kU as soon as
-// step s has been consumed, so kU 16-byte loads per lane stay in flight; during the last batch the
+// cr.lo + u of the current stream `cp` (u < U); every register is refilled with step s + kU as soon as
+// step s has been consumed, so U 16-byte loads per lane stay in flight; during the last batch the
 // refills switch to the warp's NEXT task (`nxp`, kind NT, steps `nr`; possibly in a later phase, behind
-// a __syncthreads; nullptr: no next task), whose first kU steps are therefore already in flight when
+// a __syncthreads; nullptr: no next task), whose first U steps are therefore already in flight when
 // it starts.  Result: c0, c1 = y[chain 2c], y[chain 2c+1] at block element g (lane = 4g + c).
-template <bool SUB, int CT, int NT>
-__device__ __forceinline__ void mma_task(double2 (&a)[kU], const double* cp, StepRange cr, const double* nxp,
+template <bool SUB, int CT, int NT, int U>
+__device__ __forceinline__ void mma_task(double2 (&a)[U], const double* cp, StepRange cr, const double* nxp,
                                          StepRange nr, const double* x, const double* xsub, int ns, int np,
                                          double& c0, double& c1) {
   const int lane = threadIdx.x & 31;
   const size_t bo = (size_t)(lane >> 2) * ns + 2 * (lane & 3);
   const double* bp = x + bo;
   const double* bs = SUB ? xsub + bo : nullptr;
-  const int nsteps = cr.hi - cr.lo;
-  const int nlast = cr.lo + ((nsteps - 1) / kU) * kU;  // first step of the last batch
+  const int nhi = nxp != nullptr ? nr.hi : 0;
   double acc[2][2];  // two independent accumulator pairs (even / odd k-group of a step)
 #pragma unroll
   for (int q = 0; q < 2; ++q) acc[q][0] = acc[q][1] = 0.0;
-  auto consume = [&](int s, int u) {
-    double2 b = *reinterpret_cast<const double2*>(bp + 8 * s);
-    if (SUB) {
-      const double2 b2 = *reinterpret_cast<const double2*>(bs + 8 * s);
-      b.x -= b2.x;
-      b.y -= b2.y;
-    }
-    dmma(acc[0][0], acc[0][1], a[u].x, b.x);
-    dmma(acc[1][0], acc[1][1], a[u].y, b.y);
-  };
+  // one loop body for all batches (code size): the refill of slot u comes from the current stream while
+  // it has steps left, else from the next task (an empty current range falls straight through)
 #pragma unroll 1
-  for (int s0 = cr.lo; s0 < nlast; s0 += kU) {
+  for (int s0 = cr.lo; s0 < cr.hi || s0 == cr.lo; s0 += U) {
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      consume(s0 + u, u);
-      a[u] = load_step<CT>(cp, s0 + u + kU, cr.hi, np);
+    for (int u = 0; u < U; ++u) {
+      const int s = s0 + u;
+      if (s < cr.hi) {
+        double2 b = *reinterpret_cast<const double2*>(bp + 8 * s);
+        if (SUB) {
+          const double2 b2 = *reinterpret_cast<const double2*>(bs + 8 * s);
+          b.x -= b2.x;
+          b.y -= b2.y;
+        }
+        dmma(acc[0][0], acc[0][1], a[u].x, b.x);
+        dmma(acc[1][0], acc[1][1], a[u].y, b.y);
+      }
+      const int sn = s + U;
+      if (s0 + U < cr.hi) {
+        a[u] = load_step<CT>(cp, sn, cr.hi, np);            // not the last batch: keep streaming
+      } else {
+        a[u] = load_step<NT>(nxp, nr.lo + u, nhi, np);      // last batch: first steps of the next task
+      }
     }
-  }
-  const int nhi = nxp != nullptr ? nr.hi : 0;
-#pragma unroll
-  for (int u = 0; u < kU; ++u) {
-    if (nlast + u < cr.hi) consume(nlast + u, u);
-    a[u] = load_step<NT>(nxp, nr.lo + u, nhi, np);
   }
   c0 = acc[0][0] + acc[1][0];
   c1 = acc[0][1] + acc[1][1];

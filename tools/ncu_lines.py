@@ -12,7 +12,13 @@ import os
 
 rep, obj, pat = sys.argv[1:4]
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".csv.gz"):
+    import gzip
+    out = gzip.open(rep, "rt").read()
+elif rep.endswith(".csv"):
+    out = open(rep).read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = None
 sass = []
