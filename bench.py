@@ -235,6 +235,8 @@ def run_b200(args):
     t_setup = time.perf_counter()
     prob, info, state, data = synth.sweep_problem(B, R, dev, seed0=rank * B, model="seir4", bandsize=80)
     assert int(info.abs().max()) == 0, "factorisation reported a non-positive-definite matrix"
+    if os.environ.get("MAGI_BENCH_DENSE"):      # experiment: read the (banded) matrices as if dense
+        prob.band = -1
     pin = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).pin_memory()
     hX, hs, ht = pin(state["X"]), pin(state["sig_pre"]), pin(state["th_pre"])
     hbt = pin(np.full((B, R), 0.37))

@@ -526,7 +526,7 @@ int launch_logpost(const magi_problem_t* pb, const double* X, const double* sig_
       auto kern = np == kFastMaxNp ? logpost_grad_fast_kernel<M, kFastMaxNp> : logpost_grad_fast_kernel<M, 0>;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return magi_cuda_status(e);
-      kern<<<fast_grid(pb), 32 * ((np / 8 + 1) / 2), smem, st>>>(*pb, X, sig_pre, th_pre, beta_temp, lp, gX, gsig, gth);
+      kern<<<fast_grid(pb), 32 * (np / 8), smem, st>>>(*pb, X, sig_pre, th_pre, beta_temp, lp, gX, gsig, gth);
       return magi_cuda_status(cudaGetLastError());
     }
   }
@@ -557,7 +557,7 @@ int launch_leapfrog(const magi_problem_t* pb, double* X, double* sig_pre, double
       auto kern = np == kFastMaxNp ? leapfrog_fast_kernel<M, kFastMaxNp> : leapfrog_fast_kernel<M, 0>;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return magi_cuda_status(e);
-      kern<<<grid, 32 * ((np / 8 + 1) / 2), smem, st>>>(*pb, X, sig_pre, th_pre, pX, psig, pth, eps, beta_temp, n_steps, lp_out,
+      kern<<<grid, 32 * (np / 8), smem, st>>>(*pb, X, sig_pre, th_pre, pX, psig, pth, eps, beta_temp, n_steps, lp_out,
                                              static_cast<double*>(ws));
       return magi_cuda_status(cudaGetLastError());
     }
@@ -586,7 +586,7 @@ int launch_hmc(const magi_problem_t* pb, const magi_hmc_config_t* cfg, double* X
       auto kern = np == kFastMaxNp ? hmc_fast_kernel<M, kFastMaxNp> : hmc_fast_kernel<M, 0>;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return magi_cuda_status(e);
-      kern<<<grid, 32 * ((np / 8 + 1) / 2), smem, st>>>(*pb, *cfg, X, sig_pre, th_pre, eps, da_state, out,
+      kern<<<grid, 32 * (np / 8), smem, st>>>(*pb, *cfg, X, sig_pre, th_pre, eps, da_state, out,
                                              static_cast<double*>(ws));
       return magi_cuda_status(cudaGetLastError());
     }

@@ -35,7 +35,7 @@ __device__ __forceinline__ const double* fast_mats(const magi_problem_t& pb, int
 
 // ---- (3b) log-posterior + gradient ---------------------------------------------------------------
 template <class M, int NP>
-__global__ void __launch_bounds__(kFastMaxThreads, 1)
+__global__ void __launch_bounds__(kMaxThreads, 1)
 logpost_grad_fast_kernel(magi_problem_t pb, const double* __restrict__ X, const double* __restrict__ sig_pre,
                          const double* __restrict__ th_pre, const double* __restrict__ beta_temp,
                          double* __restrict__ lp, double* __restrict__ gX, double* __restrict__ gsig,
@@ -44,37 +44,28 @@ logpost_grad_fast_kernel(magi_problem_t pb, const double* __restrict__ X, const 
   FastScratch<M, NP> S;
   fast_setup<M, NP>(S, pb.n);
   const int n = S.n, np = S.np(), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const Own own = fast_own(S);
-  const int c2 = own.c2;
+  const int g = lane >> 2, c2 = 2 * (lane & 3), j = warp * 8 + g;
   int b, nr;
   size_t chain0;
-  double2 a[kFU];
+  double2 a[kU];
   if (fast_item<M>(pb, blockIdx.x, b, nr, chain0))
-    load_batch<kFwd>(a, stream_ptr<kFwd>(fast_mats<M>(pb, b, np), np, warp, lane),
-                     band_range(warp, np >> 3, band_blocks(pb.band, np >> 3)), np);
+    load_batch<kFwd>(a, stream_ptr<kFwd>(fast_mats<M>(pb, b, np), np, warp, lane), StepRange{0, np >> 3}, np);
   for (int item = blockIdx.x; fast_item<M>(pb, item, b, nr, chain0); item += gridDim.x) {
-#ifdef MAGI_EXP_SKIPLOAD
-    if (item == (int)blockIdx.x)
-#endif
     fast_load_item(S, pb, b, X, sig_pre, th_pre, chain0, nr);
     int bn, nrn;
     size_t c0n;
     const double* next_mats = fast_item<M>(pb, item + gridDim.x, bn, nrn, c0n) ? fast_mats<M>(pb, bn, np) : nullptr;
-    double gxr[2][D][2];
-    fast_eval(S, fast_mats<M>(pb, b, np), next_mats, 1.0 / pb.beta[b], pb.band, pb.y + (size_t)b * n * D,
-              pb.mask + (size_t)b * n * D, gxr, a);
+    double gxr[D][2];
+    fast_eval(S, fast_mats<M>(pb, b, np), next_mats, 1.0 / pb.beta[b], gxr, a);
     // scale by the temperature and store in the reference layout X[n][D]
+    if (j < n) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (own.j[h] < n) {
+      for (int q = 0; q < 2; ++q) {
+        if (c2 + q < nr) {
+          const double bt = beta_temp[chain0 + c2 + q];
+          double* o = gX + ((chain0 + c2 + q) * n + j) * D;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (c2 + q < nr) {
-            const double bt = beta_temp[chain0 + c2 + q];
-            double* o = gX + ((chain0 + c2 + q) * n + own.j[h]) * D;
-#pragma unroll
-            for (int d = 0; d < D; ++d) o[d] = bt * gxr[h][d][q];
-          }
+          for (int d = 0; d < D; ++d) o[d] = bt * gxr[d][q];
         }
       }
     }
@@ -94,31 +85,26 @@ logpost_grad_fast_kernel(magi_problem_t pb, const double* __restrict__ X, const 
 // p += ck * eps * bt * grad  and, if drift, z += eps * p  -- on all three state parts.  The momentum of
 // X is in the CTA's global scratch slot (own-element order), the gradient of X in registers.
 template <class M, int NP>
-__device__ __forceinline__ void fast_kick_drift(const FastScratch<M, NP>& S, double* PX,
-                                                const double (&gxr)[2][M::D][2], const double* epsv,
-                                                const double* btv, double ck, bool drift) {
+__device__ __forceinline__ void fast_kick_drift(const FastScratch<M, NP>& S, double* PX, const double (&gxr)[M::D][2],
+                                                const double* epsv, const double* btv, double ck, bool drift) {
   constexpr int D = M::D, P = M::P;
-  const int tid = threadIdx.x, nw = S.nw();
-  const Own own = fast_own(S);
-  const int c2 = own.c2;
-  const double e0 = epsv[c2], e1 = epsv[c2 + 1];
-  const double h0 = ck * e0 * btv[c2], h1 = ck * e1 * btv[c2 + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, c2 = 2 * (lane & 3), j = warp * 8 + g;
+  const int nblk = S.np() >> 3;
+  if (j < S.n) {
+    const double e0 = epsv[c2], e1 = epsv[c2 + 1];
+    const double h0 = ck * e0 * btv[c2], h1 = ck * e1 * btv[c2 + 1];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int j = own.j[h];
-    if (j < S.n) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        double2* pp = reinterpret_cast<double2*>(PX + own_ix(d, h, nw));
-        double2 p = *pp;
-        p.x = fma(h0, gxr[h][d][0], p.x);
-        p.y = fma(h1, gxr[h][d][1], p.y);
-        *pp = p;
-        if (drift) {
-          const size_t i0 = S.vix(d, c2, j), i1 = i0 + S.ns();
-          S.Xc()[i0] = fma(e0, p.x, S.Xc()[i0]);
-          S.Xc()[i1] = fma(e1, p.y, S.Xc()[i1]);
-        }
+    for (int d = 0; d < D; ++d) {
+      double2* pp = reinterpret_cast<double2*>(PX + own_ix(d, nblk));
+      double2 p = *pp;
+      p.x = fma(h0, gxr[d][0], p.x);
+      p.y = fma(h1, gxr[d][1], p.y);
+      *pp = p;
+      if (drift) {
+        const size_t i0 = S.vix(d, c2, j), i1 = i0 + S.ns();
+        S.Xc()[i0] = fma(e0, p.x, S.Xc()[i0]);
+        S.Xc()[i1] = fma(e1, p.y, S.Xc()[i1]);
       }
     }
   }
@@ -139,56 +125,38 @@ __device__ __forceinline__ void fast_kick_drift(const FastScratch<M, NP>& S, dou
   }
 }
 
-// what fast_eval needs besides the scratch: the dataset's matrices, y, mask, 1/beta, band
-struct FastData {
-  const double* mats;
-  const double* y;
-  const uint8_t* mask;
-  double inv_beta;
-  int band;
-};
-template <class M>
-__device__ __forceinline__ FastData fast_data(const magi_problem_t& pb, int b, int n, int np) {
-  return FastData{fast_mats<M>(pb, b, np), pb.y + (size_t)b * n * M::D, pb.mask + (size_t)b * n * M::D,
-                  1.0 / pb.beta[b], pb.band};
-}
-
 // TFP SimpleLeapfrogIntegrator: per step  p += eps/2 g;  z += eps p;  g = grad(z);  p += eps/2 g  (the two
-// half kicks of consecutive steps are applied as one).  Needs the gradient at the current z in gxr / S.gs /
-// S.gtau on entry; leaves the gradient at the end point.  `next_mats`: matrices whose first fragments
+// half kicks of consecutive steps are applied as one).  Needs the gradient at the current z in gxr / S.gs() /
+// S.gtau() on entry; leaves the gradient at the end point.  `next_mats`: matrices whose first fragments
 // should be in flight when the last evaluation ends (the same dataset again, the next item, or null).
 template <class M, int NP>
-__device__ void fast_leapfrog_steps(const FastScratch<M, NP>& S, double* PX, double (&gxr)[2][M::D][2],
-                                    double2 (&a)[kFU], const FastData& fd, const double* next_mats,
+__device__ void fast_leapfrog_steps(const FastScratch<M, NP>& S, double* PX, double (&gxr)[M::D][2], double2 (&a)[kU],
+                                    const double* mats, const double* next_mats, double inv_beta,
                                     const double* epsv, const double* btv, int n_steps) {
   if (n_steps <= 0) return;
   fast_kick_drift(S, PX, gxr, epsv, btv, 0.5, true);
-#pragma unroll 1
   for (int st = 0; st < n_steps; ++st) {
     const bool last = st + 1 == n_steps;
-    fast_eval(S, fd.mats, last ? next_mats : fd.mats, fd.inv_beta, fd.band, fd.y, fd.mask, gxr, a);
+    fast_eval(S, mats, last ? next_mats : mats, inv_beta, gxr, a);  // starts with a __syncthreads-protected phase
     fast_kick_drift(S, PX, gxr, epsv, btv, last ? 0.5 : 1.0, !last);
   }
   __syncthreads();
 }
 
-// out[r] = 1/2 |p_r|^2 over all three parts (fixed summation order).  Uses S.wpart.
+// out[r] = 1/2 |p_r|^2 over all three parts (fixed summation order).  Uses S.wpart() / S.tot().
 template <class M, int NP>
 __device__ void fast_kinetic(const FastScratch<M, NP>& S, const double* PX, double* out) {
   constexpr int D = M::D, P = M::P, NRED = FastScratch<M, NP>::NRED;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = S.nw();
-  const Own own = fast_own(S);
-  const int c2 = own.c2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = S.nblk();
+  const int g = lane >> 2, c2 = 2 * (lane & 3), j = warp * 8 + g;
+  const int nblk = S.nblk();
   double k0 = 0.0, k1 = 0.0;
+  if (j < S.n) {
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    if (own.j[h] < S.n) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const double2 p = *reinterpret_cast<const double2*>(PX + own_ix(d, h, nw));
-        k0 = fma(p.x, p.x, k0);
-        k1 = fma(p.y, p.y, k1);
-      }
+    for (int d = 0; d < D; ++d) {
+      const double2 p = *reinterpret_cast<const double2*>(PX + own_ix(d, nblk));
+      k0 = fma(p.x, p.x, k0);
+      k1 = fma(p.y, p.y, k1);
     }
   }
   k0 = fold_g(k0);
@@ -213,40 +181,34 @@ __device__ void fast_kinetic(const FastScratch<M, NP>& S, const double* PX, doub
 
 // ---- (3c) leapfrog with caller-supplied momenta ---------------------------------------------------
 template <class M, int NP>
-__global__ void __launch_bounds__(kFastMaxThreads, 1)
+__global__ void __launch_bounds__(kMaxThreads, 1)
 leapfrog_fast_kernel(magi_problem_t pb, double* X, double* sig_pre, double* th_pre, double* pX, double* psig,
                      double* pth, const double* __restrict__ eps, const double* __restrict__ beta_temp, int n_steps,
                      double* lp_out, double* ws) {
   constexpr int D = M::D, P = M::P;
   FastScratch<M, NP> S;
   fast_setup<M, NP>(S, pb.n);
-  const int n = S.n, np = S.np(), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = S.nw();
-  const Own own = fast_own(S);
-  const int c2 = own.c2;
+  const int n = S.n, np = S.np(), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, c2 = 2 * (lane & 3), j = warp * 8 + g, nblk = np >> 3;
   double* PX = ws + (size_t)blockIdx.x * fast_slot_elems<M>(np);
   double* epsv = S.ctl();
   double* btv = S.ctl() + kCh;
   int b, nr;
   size_t chain0;
-  double2 a[kFU];
+  double2 a[kU];
   if (fast_item<M>(pb, blockIdx.x, b, nr, chain0))
-    load_batch<kFwd>(a, stream_ptr<kFwd>(fast_mats<M>(pb, b, np), np, warp, lane),
-                     band_range(warp, np >> 3, band_blocks(pb.band, np >> 3)), np);
+    load_batch<kFwd>(a, stream_ptr<kFwd>(fast_mats<M>(pb, b, np), np, warp, lane), StepRange{0, nblk}, np);
   for (int item = blockIdx.x; fast_item<M>(pb, item, b, nr, chain0); item += gridDim.x) {
     fast_load_item(S, pb, b, X, sig_pre, th_pre, chain0, nr);
     // momenta into own-element order
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = own.j[h];
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        double2 p = make_double2(0.0, 0.0);
-        if (j < n) {
-          if (c2 < nr) p.x = pX[((chain0 + c2) * n + j) * D + d];
-          if (c2 + 1 < nr) p.y = pX[((chain0 + c2 + 1) * n + j) * D + d];
-        }
-        if (own.b[h] >= 0) *reinterpret_cast<double2*>(PX + own_ix(d, h, nw)) = p;
+    for (int d = 0; d < D; ++d) {
+      double2 p = make_double2(0.0, 0.0);
+      if (j < n) {
+        if (c2 < nr) p.x = pX[((chain0 + c2) * n + j) * D + d];
+        if (c2 + 1 < nr) p.y = pX[((chain0 + c2 + 1) * n + j) * D + d];
       }
+      *reinterpret_cast<double2*>(PX + own_ix(d, nblk)) = p;
     }
     if (tid < kCh) {
       const bool ok = tid < nr;
@@ -258,28 +220,25 @@ leapfrog_fast_kernel(magi_problem_t pb, double* X, double* sig_pre, double* th_p
       for (int k = 0; k < P; ++k) S.ptau()[k * kCh + tid] = ok ? pth[(chain0 + tid) * P + k] : 0.0;
     }
     __syncthreads();
-    const FastData fd = fast_data<M>(pb, b, n, np);
+    const double* mats = fast_mats<M>(pb, b, np);
     int bn, nrn;
     size_t c0n;
     const double* next_mats = fast_item<M>(pb, item + gridDim.x, bn, nrn, c0n) ? fast_mats<M>(pb, bn, np) : nullptr;
-    double gxr[2][D][2];
-    fast_eval(S, fd.mats, n_steps > 0 ? fd.mats : next_mats, fd.inv_beta, fd.band, fd.y, fd.mask, gxr, a);
-    fast_leapfrog_steps(S, PX, gxr, a, fd, next_mats, epsv, btv, n_steps);
+    const double inv_beta = 1.0 / pb.beta[b];
+    double gxr[D][2];
+    fast_eval(S, mats, n_steps > 0 ? mats : next_mats, inv_beta, gxr, a);
+    fast_leapfrog_steps(S, PX, gxr, a, mats, next_mats, inv_beta, epsv, btv, n_steps);
 
+    if (j < n) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = own.j[h];
-      if (j < n) {
+      for (int q = 0; q < 2; ++q) {
+        if (c2 + q < nr) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          const double2 p = *reinterpret_cast<const double2*>(PX + own_ix(d, h, nw));
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            if (c2 + q < nr) {
-              const size_t o = ((chain0 + c2 + q) * n + j) * D + d;
-              X[o] = S.Xc()[S.vix(d, c2 + q, j)] + S.mu()[d];
-              pX[o] = q ? p.y : p.x;
-            }
+          for (int d = 0; d < D; ++d) {
+            const size_t o = ((chain0 + c2 + q) * n + j) * D + d;
+            X[o] = S.Xc()[S.vix(d, c2 + q, j)] + S.mu()[d];
+            const double2 p = *reinterpret_cast<const double2*>(PX + own_ix(d, nblk));
+            pX[o] = q ? p.y : p.x;
           }
         }
       }
@@ -303,15 +262,14 @@ leapfrog_fast_kernel(magi_problem_t pb, double* X, double* sig_pre, double* th_p
 
 // ---- (3d) HMC sampler: all iterations of a group of 8 chains inside one CTA -------------------------
 template <class M, int NP>
-__global__ void __launch_bounds__(kFastMaxThreads, 1)
+__global__ void __launch_bounds__(kMaxThreads, 1)
 hmc_fast_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig_pre, double* th_pre, double* eps,
                 double* da_state, HmcOut out, double* ws) {
   constexpr int D = M::D, P = M::P;
   FastScratch<M, NP> S;
   fast_setup<M, NP>(S, pb.n);
-  const int n = S.n, np = S.np(), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = S.nw();
-  const Own own = fast_own(S);
-  const int c2 = own.c2;
+  const int n = S.n, np = S.np(), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, c2 = 2 * (lane & 3), j = warp * 8 + g, nblk = np >> 3;
   const size_t slot = fast_slot_elems<M>(np);
   double* PX = ws + (size_t)blockIdx.x * 3 * slot;   // momentum
   double* X0 = PX + slot;                            // start point of the transition (centred)
@@ -326,17 +284,16 @@ hmc_fast_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig
   double* L0 = S.ctl() + 5 * kCh;       // [8]
   double* da = S.ctl() + 6 * kCh;       // [4][8]
   double* tau0 = S.ctl() + 16 * kCh;    // [P][8]
-  double* gtau0 = tau0 + P * kCh;       // [P][8]
-  double* s0 = gtau0 + P * kCh;         // [D][8]
-  double* gs0 = s0 + D * kCh;           // [D][8]
+  double* gtau0 = tau0 + P * kCh;     // [P][8]
+  double* s0 = gtau0 + P * kCh;       // [D][8]
+  double* gs0 = s0 + D * kCh;         // [D][8]
   const int nstate = n * D + D + P;
 
   int b, nr;
   size_t chain0;
-  double2 a[kFU];
+  double2 a[kU];
   if (fast_item<M>(pb, blockIdx.x, b, nr, chain0))
-    load_batch<kFwd>(a, stream_ptr<kFwd>(fast_mats<M>(pb, b, np), np, warp, lane),
-                     band_range(warp, np >> 3, band_blocks(pb.band, np >> 3)), np);
+    load_batch<kFwd>(a, stream_ptr<kFwd>(fast_mats<M>(pb, b, np), np, warp, lane), StepRange{0, nblk}, np);
   for (int item = blockIdx.x; fast_item<M>(pb, item, b, nr, chain0); item += gridDim.x) {
     fast_load_item(S, pb, b, X, sig_pre, th_pre, chain0, nr);
     if (tid < kCh) {
@@ -346,52 +303,53 @@ hmc_fast_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig
       for (int q = 0; q < 4; ++q) da[q * kCh + tid] = ok ? da_state[(chain0 + tid) * 4 + q] : 0.0;
     }
     __syncthreads();
-    const FastData fd = fast_data<M>(pb, b, n, np);
+    const double* mats = fast_mats<M>(pb, b, np);
     int bn, nrn;
     size_t c0n;
     const double* next_mats = fast_item<M>(pb, item + gridDim.x, bn, nrn, c0n) ? fast_mats<M>(pb, bn, np) : nullptr;
-    double gxr[2][D][2];
-    fast_eval(S, fd.mats, cfg.n_iter > 0 ? fd.mats : next_mats, fd.inv_beta, fd.band, fd.y, fd.mask, gxr, a);
+    const double inv_beta = 1.0 / pb.beta[b];
+    double gxr[D][2];
+    fast_eval(S, mats, cfg.n_iter > 0 ? mats : next_mats, inv_beta, gxr, a);
 
-#pragma unroll 1
     for (int it = 0; it < cfg.n_iter; ++it) {
       const int git = cfg.iter0 + it;
       const double bt = cfg.fixed_beta_temp > 0.0 ? cfg.fixed_beta_temp
                                                   : fmax(1.0 / log((double)git + 2.0), cfg.min_temp);
       // save the start point and its gradient; draw momenta ~ N(0, I): element e of the packed state
       // (X row-major [n][D], then s, then tau) is normal number e of the chain's Philox stream
+      if (j < n) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int j = own.j[h];
-        if (j < n) {
-          double pq[D][2];
+        for (int d = 0; d < D; ++d) {
+          const size_t o = own_ix(d, nblk);
+          *reinterpret_cast<double2*>(X0 + o) = make_double2(S.Xc()[S.vix(d, c2, j)], S.Xc()[S.vix(d, c2 + 1, j)]);
+          *reinterpret_cast<double2*>(G0 + o) = make_double2(gxr[d][0], gxr[d][1]);
+        }
+        double pq[D][2];
 #pragma unroll
-          for (int d = 0; d < D; ++d) {
-            const size_t o = own_ix(d, h, nw);
-            *reinterpret_cast<double2*>(X0 + o) = make_double2(S.Xc()[S.vix(d, c2, j)], S.Xc()[S.vix(d, c2 + 1, j)]);
-            *reinterpret_cast<double2*>(G0 + o) = make_double2(gxr[h][d][0], gxr[h][d][1]);
-            pq[d][0] = pq[d][1] = 0.0;
-          }
+        for (int q = 0; q < 2; ++q) {
+          const uint32_t cid = cfg.chain_id0 + (uint32_t)(chain0 + c2 + q);
+          const int e0 = j * D;
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            if (c2 + q < nr) {
-              const uint32_t cid = cfg.chain_id0 + (uint32_t)(chain0 + c2 + q);
-              const int e0 = j * D;
-              for (int pr = e0 >> 1; pr <= (e0 + D - 1) >> 1; ++pr) {  // pairs covering elements e0 .. e0 + D - 1
-                double z0, z1;
-                magi_normal_pair(cfg.seed, (uint32_t)pr, cid, (uint32_t)git, z0, z1);
+          for (int d = 0; d < D; ++d) pq[d][q] = 0.0;
+          if (c2 + q < nr) {
+            // pairs covering elements e0 .. e0 + D - 1
+            for (int pr = e0 >> 1; pr <= (e0 + D - 1) >> 1; ++pr) {
+              double z0, z1;
+              magi_normal_pair(cfg.seed, (uint32_t)pr, cid, (uint32_t)git, z0, z1);
 #pragma unroll
-                for (int d = 0; d < D; ++d) {
-                  if (2 * pr == e0 + d) pq[d][q] = z0;
-                  if (2 * pr + 1 == e0 + d) pq[d][q] = z1;
-                }
+              for (int d = 0; d < D; ++d) {
+                if (2 * pr == e0 + d) pq[d][q] = z0;
+                if (2 * pr + 1 == e0 + d) pq[d][q] = z1;
               }
             }
           }
-#pragma unroll
-          for (int d = 0; d < D; ++d)
-            *reinterpret_cast<double2*>(PX + own_ix(d, h, nw)) = make_double2(pq[d][0], pq[d][1]);
         }
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+          *reinterpret_cast<double2*>(PX + own_ix(d, nblk)) = make_double2(pq[d][0], pq[d][1]);
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) *reinterpret_cast<double2*>(PX + own_ix(d, nblk)) = make_double2(0.0, 0.0);
       }
       if (tid < kCh) {
         btv[tid] = bt;
@@ -423,7 +381,7 @@ hmc_fast_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig
       __syncthreads();
 
       const bool last_it = it + 1 == cfg.n_iter;
-      fast_leapfrog_steps(S, PX, gxr, a, fd, last_it ? next_mats : fd.mats, epsv, btv, cfg.n_leapfrog);
+      fast_leapfrog_steps(S, PX, gxr, a, mats, last_it ? next_mats : mats, inv_beta, epsv, btv, cfg.n_leapfrog);
 
       fast_kinetic(S, PX, ke);
       if (tid < kCh) {
@@ -473,33 +431,27 @@ hmc_fast_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig
       }
       __syncthreads();
       // rejected chains go back to the start point; then emit the trajectory sample
-      {
+      if (j < n) {
         const bool acc0 = accf[c2] != 0.0, acc1 = accf[c2 + 1] != 0.0;
         const bool accum = git >= cfg.accum_from && (out.X_sum || out.X_sumsq);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int j = own.j[h];
-          if (j < n) {
+        for (int d = 0; d < D; ++d) {
+          const size_t o = own_ix(d, nblk);
+          if (!acc0 || !acc1) {
+            const double2 x0 = *reinterpret_cast<const double2*>(X0 + o);
+            const double2 g0 = *reinterpret_cast<const double2*>(G0 + o);
+            if (!acc0) { S.Xc()[S.vix(d, c2, j)] = x0.x; gxr[d][0] = g0.x; }
+            if (!acc1) { S.Xc()[S.vix(d, c2 + 1, j)] = x0.y; gxr[d][1] = g0.y; }
+          }
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-              const size_t o = own_ix(d, h, nw);
-              if (!acc0 || !acc1) {
-                const double2 x0 = *reinterpret_cast<const double2*>(X0 + o);
-                const double2 g0 = *reinterpret_cast<const double2*>(G0 + o);
-                if (!acc0) { S.Xc()[S.vix(d, c2, j)] = x0.x; gxr[h][d][0] = g0.x; }
-                if (!acc1) { S.Xc()[S.vix(d, c2 + 1, j)] = x0.y; gxr[h][d][1] = g0.y; }
-              }
-#pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                if (c2 + q < nr) {
-                  const double xv = S.Xc()[S.vix(d, c2 + q, j)] + S.mu()[d];
-                  const size_t go = ((chain0 + c2 + q) * n + j) * D + d;
-                  if (out.X_samps) out.X_samps[(size_t)it * nchains * n * D + go] = xv;
-                  if (accum) {
-                    if (out.X_sum) out.X_sum[go] += xv;
-                    if (out.X_sumsq) out.X_sumsq[go] = fma(xv, xv, out.X_sumsq[go]);
-                  }
-                }
+          for (int q = 0; q < 2; ++q) {
+            if (c2 + q < nr) {
+              const double xv = S.Xc()[S.vix(d, c2 + q, j)] + S.mu()[d];
+              const size_t go = ((chain0 + c2 + q) * n + j) * D + d;
+              if (out.X_samps) out.X_samps[(size_t)it * nchains * n * D + go] = xv;
+              if (accum) {
+                if (out.X_sum) out.X_sum[go] += xv;
+                if (out.X_sumsq) out.X_sumsq[go] = fma(xv, xv, out.X_sumsq[go]);
               }
             }
           }
@@ -509,17 +461,13 @@ hmc_fast_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig
     }
 
     // write back the chain state
+    if (j < n) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = own.j[h];
-      if (j < n) {
+      for (int q = 0; q < 2; ++q) {
+        if (c2 + q < nr) {
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (c2 + q < nr) {
-#pragma unroll
-            for (int d = 0; d < D; ++d)
-              X[((chain0 + c2 + q) * n + j) * D + d] = S.Xc()[S.vix(d, c2 + q, j)] + S.mu()[d];
-          }
+          for (int d = 0; d < D; ++d)
+            X[((chain0 + c2 + q) * n + j) * D + d] = S.Xc()[S.vix(d, c2 + q, j)] + S.mu()[d];
         }
       }
     }
