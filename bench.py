@@ -283,7 +283,10 @@ def run_b200(args):
 
     # -- (2) end to end through the host-buffer entry point ---------------------------------------
     hout = prob.logpost_grad_host_out(R)
-    ms_e2e = timed(lambda: prob.logpost_grad_host(hX, hs, ht, hbt, out=hout), args.steps, max(3, args.warmup))
+    e2e_chunks = int(os.environ.get("MAGI_E2E_CHUNKS", "16"))
+    e2e_streams = int(os.environ.get("MAGI_E2E_STREAMS", "4"))
+    ms_e2e = timed(lambda: prob.logpost_grad_host(hX, hs, ht, hbt, out=hout, n_chunks=e2e_chunks,
+                                                  n_streams=e2e_streams), args.steps, max(3, args.warmup))
     e2e_value = evals_per_step * args.steps / (ms_e2e * 1e-3)
     h2d = (hX.numel() + hs.numel() + ht.numel() + hbt.numel()) * 8
     d2h = sum(t.numel() for t in hout) * 8
@@ -343,11 +346,11 @@ def run_b200(args):
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                traffic = json.load(f).get("logpost_grad_kernel_bytes_per_launch")
+                traffic = json.load(f).get("logpost_grad_fast_kernel_bytes_per_launch_4096_datasets")
         except (OSError, ValueError):
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "logpost_grad_kernel<Seir4>", "peak_source": peak_src,
+                "traffic": traffic, "kernel": "logpost_grad_fast_kernel<Seir4, 168>", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_eval * B * R,
                 "fp64_flops_per_launch": 8.0 * D * N_GRID * N_GRID * B * R,
                 "fp64_tflops_achieved": 8.0 * D * N_GRID * N_GRID * B * R / (launch_ms * 1e-3) / 1e12,

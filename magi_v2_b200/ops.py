@@ -195,7 +195,7 @@ class PosteriorProblem:
         return mk(self.B, R), mk(self.B, R, self.n, self.D), mk(self.B, R, self.D), mk(self.B, R, self.P)
 
     def logpost_grad_host(self, X: Tensor, sig_pre: Tensor, th_pre: Tensor, beta_temp: Tensor, out=None,
-                          n_chunks: int = 8, n_streams: int = 3):
+                          n_chunks: int = 16, n_streams: int = 4):
         """Same as `logpost_grad` for HOST tensors (pinned for full speed): the batch is cut into
         dataset chunks whose host->device copy, kernel launch and device->host copy are pipelined over
         `n_streams` CUDA streams, so that PCIe in both directions overlaps the kernels.  Returns host
