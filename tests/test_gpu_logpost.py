@@ -111,3 +111,66 @@ def test_band_skipping_equals_dense(model, cuda_device):
         assert relerr(u, v) <= 1e-13
     o = mo.log_posterior_and_grad_autograd(X[3], s[3], tau[3], 0.8, c)
     assert abs(res[0][0][0, 3] - o[0]) <= TOL * abs(o[0]) and relerr(res[0][1][0, 3], o[1]) <= TOL
+
+
+def test_sirw_n321_general_path(cuda_device):
+    """Config 3 (SIRW, n = 321, D = 4, P = 5): np > 168, so the general path (vector arrays in the caller's
+    workspace) runs.  Matrices from the oracle's reference route; parity to 1e-9."""
+    rng = np.random.default_rng(33)
+    c = synth_constants("sirw", seed=12, N=81, disc=2, band=None, T=4.0)      # 4*80 + 1 = 321 grid points
+    assert c.n == 321
+    prob = device_problem([c], "sirw", cuda_device)
+    X, s, tau = random_state(c, "sirw", rng, 8, jitter=0.01)
+    bt = np.full((1, 8), 0.5)
+    lp, gX, gs, gt = _run(prob, X[None], s[None], tau[None], bt, cuda_device)
+    for r in (0, 5):
+        o = mo.log_posterior_and_grad_autograd(X[r], s[r], tau[r], 0.5, c)
+        assert abs(lp[0, r] - o[0]) <= TOL * abs(o[0])
+        assert relerr(gX[0, r], o[1]) <= TOL and relerr(gs[0, r], o[2]) <= TOL and relerr(gt[0, r], o[3]) <= TOL
+
+
+def test_lorenz96_large_grid_properties(cuda_device):
+    """Config 5 shape (Lorenz-96, D = 10) at n = 641 with device-built matrices: too large for the oracle to
+    finish in seconds, so the size-independent properties are checked -- linearity in beta_temp, independence
+    of a chain from its CTA neighbours, and agreement of banded-as-banded with banded-as-dense."""
+    import torch
+    from magi_v2_b200 import ops
+    rng = np.random.default_rng(9)
+    n, D, R = 641, 10, 8
+    I = np.linspace(0, 4, n)
+    T = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=cuda_device)
+    phi1, phi2 = rng.uniform(0.5, 2.0, (1, D)), rng.uniform(0.15, 0.3, (1, D))
+    C, Cp, Cpp = ops.cov_build(T(I), T(phi1), T(phi2), 2.01, True)
+    Cinv, m, Kinv, _, info = ops.factor_derive(C, Cp, Cpp, 160, 0.0)
+    assert int(info.abs().max()) == 0
+    packed = ops.pack_matrices(Cinv, m, Kinv)
+    mask = np.zeros((1, n, D), dtype=np.uint8); mask[:, ::8] = 1
+    y = rng.normal(2.0, 3.0, (1, n, D)) * mask
+    consts = dict(mu=T(np.full((1, D), 2.0)), y=T(y), mask=T(mask, torch.uint8), N_ds=T(np.full((1, D), 81.0)),
+                  beta=T(np.array([D * n / (81.0 * D)])), LB=T(np.full((1, D), 1e-4)), n=n)
+    X = rng.normal(2.0, 3.0, (1, R, n, D)); s = rng.normal(-1, 0.5, (1, R, D)); tau = rng.normal(2.0, 0.2, (1, R, 1))
+    res = {}
+    for band in (160, None):
+        prob = ops.PosteriorProblem("lorenz96", packed, band=band, **consts)
+        res[band] = [a.cpu().numpy() for a in prob.logpost_grad(T(X), T(s), T(tau), T(np.full((1, R), 1.0)))]
+        assert all(np.isfinite(a).all() for a in res[band])
+    for u, v in zip(res[160], res[None]):
+        assert relerr(u, v) <= 1e-12
+    prob = ops.PosteriorProblem("lorenz96", packed, band=160, **consts)
+    q = [a.cpu().numpy() for a in prob.logpost_grad(T(X), T(s), T(tau), T(np.full((1, R), 0.25)))]
+    for u, v in zip(res[160], q):
+        assert relerr(0.25 * u, v) <= 1e-14
+    perm = rng.permutation(R)
+    p = [a.cpu().numpy() for a in prob.logpost_grad(T(X[:, perm]), T(s[:, perm]), T(tau[:, perm]),
+                                                    T(np.full((1, R), 1.0)))]
+    for u, v in zip(res[160], p):   # (general path: chains 0-4 are summed by 3 warps, 5-7 by 2 -> not bit-identical)
+        assert relerr(u[0][perm], v[0]) <= 1e-13
+    # and against an independent float64 numpy evaluation of the same formula with the device-built matrices
+    from oracle import magi_oracle as mo2
+    idx = np.where(mask[0].reshape(-1) > 0)[0]
+    oc = mo2.PosteriorConstants(I=I.reshape(-1, 1), mu_ds=np.full(D, 2.0), C_d_invs=Cinv[0].cpu().numpy(),
+                                m_ds=m[0].cpu().numpy(), K_d_invs=Kinv[0].cpu().numpy(), N_ds=np.full(D, 81.0),
+                                not_nan_idxs=idx, not_nan_cols=idx % D, y_tau_ds_observed=y[0].reshape(-1)[idx],
+                                beta=float(D * n / (81.0 * D)), sigma_sqs_LB=np.full(D, 1e-4), f_vec=mo2.f_lorenz96)
+    o = mo2.log_posterior_and_grad_autograd(X[0, 2], s[0, 2], tau[0, 2], 1.0, oc)
+    assert abs(res[160][0][0, 2] - o[0]) <= TOL * abs(o[0]) and relerr(res[160][1][0, 2], o[1]) <= TOL
