@@ -274,15 +274,23 @@ __device__ void fast_load_item(const FastScratch<M, NP>& S, const magi_problem_t
     S.Y()[e] = yv;
     S.MK()[e] = mk;
   }
-#pragma unroll 1
-  for (size_t e = tid; e < 2 * S.vsz() + (size_t)2 * kCh * S.ns(); e += nthr) S.Xc()[e] = 0.0;
-  __syncthreads();
-  const int per = n * D;
-#pragma unroll 1
-  for (int e = tid; e < nr * per; e += nthr) {
-    const int r = e / per, rem = e - r * per;
-    const int jj = rem / D, d = rem - jj * D;
-    S.Xc()[S.vix(d, r, jj)] = X[(chain0 + r) * per + rem] - S.mu()[d];
+  // chain states at the own elements (lane 4g+c: grid index 8*warp + g of chains 2c, 2c+1): 32 contiguous
+  // bytes per (chain, j) for D = 4.  Every (chain, j < np) entry of Xc is written -- zeros for chains >= nr
+  // and for the padding j >= n (B-operand padding must be finite); FG, Wa, Wb are fully rewritten by every
+  // evaluation, so nothing needs clearing.
+  {
+    const int lane = tid & 31, warp = tid >> 5, j = warp * 8 + (lane >> 2), c2 = 2 * (lane & 3);
+    double mu[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) mu[d] = pb.mu[(size_t)b * D + d];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int ch = c2 + q;
+      const bool ok = ch < nr && j < n;
+      const double* xp = X + ((chain0 + (ok ? ch : 0)) * n + (ok ? j : 0)) * D;
+#pragma unroll
+      for (int d = 0; d < D; ++d) S.Xc()[S.vix(d, ch, j)] = ok ? xp[d] - mu[d] : 0.0;
+    }
   }
   if (tid < kCh * D) {
     const int r = tid / D, d = tid - r * D;
