@@ -133,14 +133,25 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 constexpr int kFwd = 0, kTr = 1, kNone = -1;
 
 // Packed matrices are stored TILED: [row block rb][column step s] tiles of 8 x 8 doubles (512 B, row-major
-// inside the tile), so that one warp-wide 128-bit load of a forward stream reads one whole contiguous
-// tile (lane l <- bytes 16 l .. 16 l + 15) and a warp streams 8 rows of a matrix as one contiguous run
-// of np/8 tiles -- DRAM-page friendly.  A transposed stream reads the tiles of one block COLUMN
-// (stride np/8 tiles), two 8-byte loads per lane per tile.
+// inside the tile), so that one warp-wide 128-bit load reads one whole contiguous tile (lane l <- bytes
+// 16 l .. 16 l + 15, i.e. T[g][2c], T[g][2c+1]) and a warp streams 8 rows of a matrix as one contiguous run
+// of np/8 tiles.  A transposed stream reads the tiles of one block COLUMN (stride np/8 tiles) with the
+// same coalesced load and transposes the fragment in registers (transpose_frag) when it is consumed.
 template <int TR>
 __device__ __forceinline__ const double* stream_ptr(const double* A, int np, int blk, int lane) {
-  return TR == kTr ? A + (size_t)blk * 64 + 16 * (lane & 3) + (lane >> 2)
-                   : A + (size_t)blk * (np >> 3) * 64 + 2 * lane;
+  return TR == kTr ? A + (size_t)blk * 64 + 2 * lane : A + (size_t)blk * (np >> 3) * 64 + 2 * lane;
+}
+
+// Lane 4g+c holds (T[g][2c], T[g][2c+1]) of an 8x8 tile; returns (T[2c][g], T[2c+1][g]) -- the A fragments
+// of the two k=4 contractions of a TRANSPOSED product.  Three 64-bit shuffles: a 2x2 exchange between the
+// lanes of rows 2r / 2r+1, then one gather.
+__device__ __forceinline__ double2 transpose_frag(double2 t) {
+  const int lane = threadIdx.x & 31;
+  const bool odd = (lane >> 2) & 1;
+  const double recv = magi_shfl_xor(odd ? t.x : t.y, 4);
+  const double2 w = odd ? make_double2(recv, t.y) : make_double2(t.x, recv);  // even row: (x, x') ; odd row: (y, y')
+  const int src = ((2 * (lane & 3) + ((lane >> 2) & 1)) << 2) | (lane >> 3);
+  return make_double2(__shfl_sync(MAGI_FULL_MASK, w.x, src), __shfl_sync(MAGI_FULL_MASK, w.y, src));
 }
 
 __device__ __forceinline__ double2 ldg_f64x2(const double* p) {
@@ -186,12 +197,7 @@ template <int TR>
 __device__ __forceinline__ double2 load_step(const double* p, int s, int hi, int np) {
   double2 v = make_double2(0.0, 0.0);
   if (s < hi) {
-    if (TR == kTr) {
-      v.x = ldg_f64(p + (size_t)s * (np >> 3) * 64);
-      v.y = ldg_f64(p + (size_t)s * (np >> 3) * 64 + 8);
-    } else {
-      v = ldg_f64x2(p + 64 * s);
-    }
+    v = ldg_f64x2(TR == kTr ? p + (size_t)s * (np >> 3) * 64 : p + 64 * s);
   }
   return v;
 }
@@ -229,8 +235,9 @@ __device__ __forceinline__ void mma_task(double2 (&a)[U], const double* cp, Step
       b.x -= b2.x;
       b.y -= b2.y;
     }
-    dmma(acc[0][0], acc[0][1], a[u].x, b.x);
-    dmma(acc[1][0], acc[1][1], a[u].y, b.y);
+    const double2 av = CT == kTr ? transpose_frag(a[u]) : a[u];
+    dmma(acc[0][0], acc[0][1], av.x, b.x);
+    dmma(acc[1][0], acc[1][1], av.y, b.y);
   };
   // all batches but the last: refill from the current stream.  (Two copies of the body on purpose: with
   // compile-time ranges every predicate folds away, which measured ~20 % faster than one shared body.)
