@@ -170,9 +170,10 @@ factor_kernel(const double* __restrict__ C, const double* __restrict__ Cp, const
   FactorSmem& sm = *reinterpret_cast<FactorSmem*>(smraw);
   const int tid = threadIdx.x;
   const size_t nn = (size_t)n * n;
-  double* Lf = ws + (size_t)blockIdx.x * (2 * nn + (size_t)kNB * n);
+  double* Lf = ws + (size_t)blockIdx.x * (3 * nn + (size_t)kNB * n);
   double* Linv = Lf + nn;
-  double* T = Linv + nn;
+  double* W = Linv + nn;
+  double* T = W + nn;
   for (int mat = blockIdx.x; mat < nmat; mat += gridDim.x) {
     const double* c = C + mat * nn;
     const double* cp = Cp + mat * nn;
@@ -192,12 +193,15 @@ factor_kernel(const double* __restrict__ C, const double* __restrict__ Cp, const
     if (tid == 0) sm.info = 0;
     // C^-1 = Linv^T Linv
     cta_gemm(n, n, n, 1.0, Linv, 1, n, Linv, n, 1, 0.0, ci, n, sm);
-    // m = C' C^-1
-    cta_gemm(n, n, n, 1.0, cp, n, 1, ci, n, 1, 0.0, mo, n, sm);
-    // K = C'' - m C'^T   (held in the Kinv buffer until factorised)
+    // W = L^-1 C'^T.  m and K are formed from W rather than through the explicit inverse:
+    //   m = C' C^-1 = W^T L^-1 ,   K = C'' - C' C^-1 C'^T = C'' - W^T W
+    // -- the subtraction of a Gram matrix keeps K symmetric positive definite to rounding, where
+    // C'' - (C' C^-1) C'^T loses eps * cond(C) (non-PD pivots at n = 1281 without jitter).
+    cta_gemm(n, n, n, 1.0, Linv, n, 1, cp, 1, n, 0.0, W, n, sm);
+    cta_gemm(n, n, n, 1.0, W, 1, n, Linv, n, 1, 0.0, mo, n, sm);
     for (size_t e = tid; e < nn; e += kFT) ki[e] = cpp[e];
     __syncthreads();
-    cta_gemm(n, n, n, -1.0, mo, n, 1, cp, 1, n, 1.0, ki, n, sm);
+    cta_gemm(n, n, n, -1.0, W, 1, n, W, n, 1, 1.0, ki, n, sm);
     // symmetrise K (the factorisation reads the lower triangle), keep a copy if asked for
     for (size_t e = tid; e < nn; e += kFT) {
       const int i = (int)(e / n), j = (int)(e % n);
@@ -235,7 +239,7 @@ extern "C" size_t magi_b200_factor_workspace_bytes(int nmat, int n) {
   if (nmat <= 0 || n <= 0) return 0;
   // sized for the largest grid any device in the box would get (2 CTAs per SM, <= 148 SMs on B200);
   // the launch clamps its grid to what this many bytes can serve.
-  const size_t per = (2 * (size_t)n * n + (size_t)kNB * n) * sizeof(double);
+  const size_t per = (3 * (size_t)n * n + (size_t)kNB * n) * sizeof(double);
   const int g = nmat < 296 ? nmat : 296;
   return per * g;
 }
@@ -254,7 +258,7 @@ extern "C" int magi_b200_factor_derive(const double* C, const double* Cp, const 
   if (!m) return -9;
   if (!Kinv) return -10;
   if (!info) return -12;
-  const size_t per = (2 * (size_t)n * n + (size_t)kNB * n) * sizeof(double);
+  const size_t per = (3 * (size_t)n * n + (size_t)kNB * n) * sizeof(double);
   int grid = factor_grid(nmat);
   if (!workspace || workspace_bytes < per) return -13;
   if ((size_t)grid * per > workspace_bytes) grid = (int)(workspace_bytes / per);

@@ -68,7 +68,7 @@ if __name__ == "__main__":
         run("seir4", 4, 3, 161, 4096, 8, 80)
         run("seir4", 4, 3, 161, 20, 8, 80)
         run("sirw", 4, 5, 321, 512, 8, None)
-    for jit in (0.0, 1e-12, 1e-10, 1e-8):
+    for jit in (0.0, 1e-12, 1e-10, 1e-8):   # (needed 1e-8 before K was formed as C'' - W^T W)
         try:
             run("lorenz96", 10, 1, 1281, 2, 64, None, steps=3, L=4, jitter=jit)
             run("lorenz96", 10, 1, 1281, 8, 8, None, steps=3, L=4, jitter=jit)
