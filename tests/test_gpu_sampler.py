@@ -109,3 +109,48 @@ def test_rng_stream_matches_oracle(cuda_device):
     torch.cuda.synchronize()
     assert np.allclose(dX.cpu().numpy()[0], X, rtol=0, atol=1e-15)   # (X - mu) + mu rounding only
     assert np.allclose(out["accept_prob"].cpu().numpy(), 1.0)
+
+
+def test_posterior_means_within_monte_carlo_error(cuda_device):
+    """north_star: 'posterior means of theta within Monte Carlo standard error'.  64 CUDA chains and 8
+    independently seeded oracle (CPU) chains sample the same untempered posterior of a small SEIR3 problem;
+    the theta and sigma^2 means must agree within 5 combined standard errors (between-chain estimates)."""
+    import torch
+    model = "seir3"
+    c = synth_constants(model, seed=77, N=9, nan_frac=0.0)
+    prob = device_problem([c], model, cuda_device)
+    n, D, P = c.n, prob.D, prob.P
+    rng = np.random.default_rng(4)
+    R, burn, keep, L, eps0 = 64, 300, 700, 16, 2e-3
+    X, s, tau = random_state(c, model, rng, R, jitter=0.005)
+    s[:] = -5.0 + 0.1 * rng.standard_normal(s.shape)
+    tau[:] = 0.5 + 0.1 * rng.standard_normal(tau.shape)
+    dX, ds, dt = _T(X[None], cuda_device), _T(s[None], cuda_device), _T(tau[None], cuda_device)
+    eps = torch.full((1, R), eps0, dtype=torch.float64, device=cuda_device)
+    da = torch.zeros((1, R, 4), dtype=torch.float64, device=cuda_device)
+    da[..., 2] = float(np.log(10.0 * eps0))
+    prob.hmc_run_(dX, ds, dt, eps, da, n_iter=burn, n_leapfrog=L, num_adapt=240, seed=11, fixed_beta_temp=1.0,
+                  keep_theta=False, keep_sigma=False)
+    out = prob.hmc_run_(dX, ds, dt, eps, da, n_iter=keep, n_leapfrog=L, iter0=burn, num_adapt=240, seed=11,
+                        fixed_beta_temp=1.0)
+    torch.cuda.synchronize()
+    th_g = out["thetas_samps"].cpu().numpy()[:, 0]            # [keep, R, P]
+    sg_g = out["sigma_sqs_samps"].cpu().numpy()[:, 0]
+    assert 0.5 < float(out["accept_prob"].mean()) < 0.98
+    # oracle chains: same algorithm, different seed (-> independent draws), fewer and shorter
+    Rc, burn_c, keep_c = 8, 200, 400
+    th_c, sg_c = [], []
+    for r in range(Rc):
+        z0 = mo.pack_state(X[r], s[r], tau[r])
+        zs, accs, _, _ = mo.hmc_chain(c, model, z0, burn_c + keep_c, L, eps0, seed=999, chain_id=r,
+                                      num_adaptation_steps=160, fixed_beta_temp=1.0)
+        Xo, so, to = zip(*[mo.unpack_state(z, n, D, P) for z in zs[burn_c:]])
+        th_c.append(np.logaddexp(0, np.array(to)))
+        sg_c.append(np.logaddexp(0, np.array(so)) + c.sigma_sqs_LB)
+    th_c, sg_c = np.array(th_c), np.array(sg_c)               # [Rc, keep_c, .]
+    for g, cc, nm in ((th_g, th_c, "theta"), (np.log(sg_g), np.log(sg_c), "log sigma^2")):
+        mg, mc = g.mean(axis=0), cc.mean(axis=1)              # per-chain means [R, k], [Rc, k]
+        se = np.sqrt(mg.var(axis=0, ddof=1) / R + mc.var(axis=0, ddof=1) / Rc)
+        z = (mg.mean(axis=0) - mc.mean(axis=0)) / se
+        print(nm, "cuda", mg.mean(axis=0), "oracle", mc.mean(axis=0), "z", z)
+        assert np.all(np.abs(z) < 5.0), (nm, z)
