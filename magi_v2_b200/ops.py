@@ -217,7 +217,10 @@ class PosteriorProblem:
             start = torch.cuda.Event()
             start.record(cur)
             n_chunks = max(1, min(n_chunks, self.B))
-            bounds = [self.B * c // n_chunks for c in range(n_chunks + 1)]
+            # equal dataset chunks (whole-wave chunks of the persistent grid measured slower: 5.7 M vs 7.5 M evals/s)
+            per = -(-self.B // n_chunks)
+            bounds = list(range(0, self.B, per)) + [self.B]
+            n_chunks = len(bounds) - 1
             for c in range(n_chunks):
                 b0, b1 = bounds[c], bounds[c + 1]
                 if b1 == b0:
@@ -227,7 +230,7 @@ class PosteriorProblem:
                 with torch.cuda.stream(stq):
                     for d_t, h_t in zip(H["in"], (X, sig_pre, th_pre, beta_temp)):
                         d_t[b0:b1].copy_(h_t[b0:b1], non_blocking=True)
-                    ws, nb = self.workspace(R, slot=1 + c % len(H["streams"]), n_datasets=bounds[1] + 1)
+                    ws, nb = self.workspace(R, slot=1 + c % len(H["streams"]), n_datasets=per + 1)
                     pb = self.struct(R, b0, b1)
                     dX, ds, dt, dbt = (t[b0:b1] for t in H["in"])
                     lp, gX, gs, gt = (t[b0:b1] for t in H["out"])
