@@ -30,9 +30,11 @@ constexpr int kCh = MAGI_CHAINS_PER_CTA;    // 8
 #endif
 constexpr int kU = MAGI_KU;                 // 8-column steps per register batch (kU x 16 B per lane in flight)
 
-// chain stride of the shared-memory vector arrays: np + 2 doubles, so that the 128-bit B-fragment
-// loads of a quarter warp (2 chains x 4 column pairs) fall into 32 distinct banks
-__host__ __device__ static inline int magi_chain_stride(int np) { return np + 2; }
+// chain stride of the shared-memory vector arrays, ns = 8 (mod 16) doubles: the 128-bit B-fragment loads are
+// served a quarter warp at a time (lanes 4g+c, g in {2q, 2q+1}: two chains x four 16-byte column pairs);
+// with the odd chain 64 B (mod 128 B) away from the even one the 8 lanes cover all 32 banks exactly once.
+// (ns = np + 2 was measured 2-way conflicted on every B load: ncu "L1 Wavefronts Shared Excessive".)
+__host__ __device__ static inline int magi_chain_stride(int np) { return (np & 15) == 8 ? np : np + 8; }
 
 // Scratch arrays of one CTA.  Vector arrays are [D][8][ns] (chain-major, grid index fastest).
 template <class M>
