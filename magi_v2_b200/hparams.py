@@ -31,6 +31,36 @@ def fourier_prior(X_filled: np.ndarray):
     return mu_phi2, (1 - mu_phi2) / 3
 
 
+def objective_and_grad(v, grid, dt, xc, loc, scale):
+    """Per (dataset, component): log N(x; mu 1, phi1 R(phi2) + (sigma^2 + jitter) I) + the three normal prior
+    terms, as a function of the softplus pre-activations v [3,B,D] = (phi1, phi2, sigma^2), and the gradient of
+    its NEGATIVE (the Adam loss) with respect to v.  Closed form:
+    d ll / d h = 1/2 tr((a a^T - S^-1) dS/dh), a = S^-1 (x - mu); dS/dphi1 = C/phi1, dS/dsigma^2 = I,
+    dS/dphi2 = -C'_{ij} (s_i - s_j)/phi2 with C, C' from torch.ops.magi_b200.cov_build."""
+    import torch
+    from . import ops
+    n = grid.shape[0]
+    eye = torch.eye(n, dtype=torch.float64, device=v.device)
+    h = torch.nn.functional.softplus(v)
+    phi1, phi2, sig2 = h[0].contiguous(), h[1].contiguous(), h[2]
+    C, Cp, _ = ops.cov_build(grid, phi1, phi2, NU, False)
+    S = C + (sig2 + JITTER)[..., None, None] * eye
+    L, info = torch.linalg.cholesky_ex(S)
+    Sinv = torch.cholesky_inverse(L)
+    a = (Sinv @ xc[..., None])[..., 0]                                          # [B,D,n]
+    W = a[..., :, None] * a[..., None, :] - Sinv
+    g_phi1 = 0.5 * (W * C).sum(dim=(-1, -2)) / phi1
+    g_sig2 = 0.5 * torch.diagonal(W, dim1=-2, dim2=-1).sum(-1)
+    g_phi2 = 0.5 * (W * (-Cp * dt)).sum(dim=(-1, -2)) / phi2
+    g = torch.stack([g_phi1, g_phi2, g_sig2])
+    g = g - (h - loc) / scale ** 2                                              # truncated-normal priors
+    g = -g * torch.sigmoid(v)                                                   # loss = -log_prob; softplus chain rule
+    ll = (-0.5 * (xc * a).sum(-1) - torch.log(torch.diagonal(L, dim1=-2, dim2=-1)).sum(-1)
+          - 0.5 * n * np.log(2 * np.pi))
+    obj = ll - 0.5 * (((h - loc) / scale) ** 2).sum(0)
+    return obj, g
+
+
 def fit_kernel_hparams(I: np.ndarray, X_filled: np.ndarray, device="cuda:0", num_iters: int = 1000,
                        lr: float = 0.01, verbose: bool = False):
     """I [n]; X_filled [B, n, D] (no NaNs).  Returns dict of phi1s, phi2s, sigma_sqs, each [B, D]."""
@@ -54,32 +84,16 @@ def fit_kernel_hparams(I: np.ndarray, X_filled: np.ndarray, device="cuda:0", num
     dt = grid[:, None] - grid[None, :]                                         # s_i - s_j
     x = T(np.transpose(X_filled, (0, 2, 1)))                                    # [B,D,n]
     xc = x - x.mean(dim=-1, keepdim=True)                                       # mean_fn = column mean (:559, :589)
-    eye = torch.eye(n, dtype=torch.float64, device=dev)
     m1 = torch.zeros_like(v)
     m2 = torch.zeros_like(v)
     b1, b2, eps = 0.9, 0.999, 1e-7                                              # tf_keras Adam defaults
     for t in range(1, num_iters + 1):
-        h = torch.nn.functional.softplus(v)
-        phi1, phi2, sig2 = h[0].contiguous(), h[1].contiguous(), h[2]
-        C, Cp, _ = ops.cov_build(grid, phi1, phi2, NU, False)
-        S = C + (sig2 + JITTER)[..., None, None] * eye
-        L, info = torch.linalg.cholesky_ex(S)
-        Sinv = torch.cholesky_inverse(L)
-        a = (Sinv @ xc[..., None])[..., 0]                                      # [B,D,n]
-        W = a[..., :, None] * a[..., None, :] - Sinv
-        g_phi1 = 0.5 * (W * C).sum(dim=(-1, -2)) / phi1
-        g_sig2 = 0.5 * torch.diagonal(W, dim1=-2, dim2=-1).sum(-1)
-        g_phi2 = 0.5 * (W * (-Cp * dt)).sum(dim=(-1, -2)) / phi2
-        g = torch.stack([g_phi1, g_phi2, g_sig2])
-        g = g - (h - loc) / scale ** 2                                          # truncated-normal priors
-        g = -g * torch.sigmoid(v)                                               # loss = -log_prob; chain rule of softplus
+        obj, g = objective_and_grad(v, grid, dt, xc, loc, scale)
         m1 = b1 * m1 + (1 - b1) * g
         m2 = b2 * m2 + (1 - b2) * g * g
         lr_t = lr * np.sqrt(1 - b2 ** t) / (1 - b1 ** t)
         v = v - lr_t * m1 / (torch.sqrt(m2) + eps)
         if verbose and (t % 100 == 0 or t == 1):
-            ll = (-0.5 * (xc * a).sum(-1) - torch.log(torch.diagonal(L, dim1=-2, dim2=-1)).sum(-1)
-                  - 0.5 * n * np.log(2 * np.pi))
-            print(f"[hparams] iter {t}: mean GP log-lik {float(ll.mean()):.4f}")
+            print(f"[hparams] iter {t}: mean objective {float(obj.mean()):.4f}")
     h = torch.nn.functional.softplus(v).cpu().numpy()
     return {"phi1s": h[0], "phi2s": h[1], "sigma_sqs": h[2]}
