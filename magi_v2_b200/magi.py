@@ -144,9 +144,13 @@ class MAGI_v2:
     # ------------------------------------------------------------------------------------------
     def predict(self, num_results: int = 1000, num_burnin_steps: int = 1000, sigma_sqs_LB=None, verbose=False,
                 n_chains: int = 1, n_leapfrog: int = 32, seed: int = 0, step_size: float = None,
-                init_jitter: float = 0.0):
+                init_jitter: float = 0.0, sampler: str = "hmc", max_tree_depth: int = 10):
         """magi_v2.py:286-425.  Returns the reference's result dictionary; with n_chains > 1 the sample
-        arrays gain a leading chain axis."""
+        arrays gain a leading chain axis.  sampler = "hmc": fixed-length trajectories, the whole chain inside the
+        fused CUDA kernel; sampler = "nuts": the reference's sampler (No-U-Turn trees, `nuts.py`) with one launch
+        of the log-posterior + gradient kernel per leapfrog step."""
+        if sampler not in ("hmc", "nuts"):
+            raise ValueError("sampler must be 'hmc' or 'nuts'")
         torch = _require_cuda()
         from . import ops
         assert ~np.any(np.isnan(self.Xhat_init)), "Please make sure Xhat_init does not have NaNs."
@@ -187,6 +191,9 @@ class MAGI_v2:
         da = torch.zeros((1, R, 4), dtype=torch.float64, device=dev)
         da[..., 2] = float(np.log(10.0 * eps0))
         num_adapt = int(0.8 * num_burnin_steps)                                                     # :365
+        if sampler == "nuts":
+            return self._predict_nuts(prob, X, s, tau, eps, da, num_results, num_burnin_steps, num_adapt, seed,
+                                      sigma_sqs_LB, max_tree_depth, verbose)
         if verbose:
             print("Starting HMC posterior sampling ...")
         start = time.time()
@@ -213,6 +220,45 @@ class MAGI_v2:
                 "kernel_results": kernel_results,
                 "sample_results": [X_s, np.log(np.expm1(np.maximum(sig_s - sigma_sqs_LB, 1e-300))),
                                    np.log(np.expm1(th_s))],
+                "minutes_elapsed": minutes}
+
+    def _predict_nuts(self, prob, X, s, tau, eps, da, num_results, num_burnin_steps, num_adapt, seed, sigma_sqs_LB,
+                      max_tree_depth, verbose):
+        """The reference's sampler stack (magi_v2.py:357-396): NUTS in dual averaging in the annealing wrapper."""
+        import torch
+        from . import nuts
+        R, n, D, P = X.shape[1], self.mag_I, self.D, self.D_thetas
+        z = nuts.pack_state(X, s, tau)
+        e, d = eps.reshape(-1).clone(), da.reshape(-1, 4).clone()
+        vg = nuts.problem_value_and_grad(prob, R)
+        if verbose:
+            print("Starting NUTS posterior sampling ...")
+        start = time.time()
+        burn = nuts.nuts_run_(z, e, d, vg, n_iter=num_burnin_steps, iter0=0, num_adapt=num_adapt, seed=seed,
+                              max_tree_depth=max_tree_depth)
+        keep = torch.empty((num_results,) + tuple(z.shape), dtype=torch.float64, device=z.device)
+        out = nuts.nuts_run_(z, e, d, vg, n_iter=num_results, iter0=num_burnin_steps, num_adapt=num_adapt, seed=seed,
+                             max_tree_depth=max_tree_depth, on_sample=lambda it, zz, info: keep[it].copy_(zz))
+        torch.cuda.synchronize(z.device)
+        minutes = np.round((time.time() - start) / 60, 2)
+        if verbose:
+            print(f"Finished sampling in {minutes} minutes.")
+        k = keep.cpu().numpy()                                               # [num_results, R, S]
+        sq = (lambda a: a[:, 0]) if R == 1 else (lambda a: np.moveaxis(a, 1, 0))
+        X_pre, s_pre, t_pre = sq(k[..., :n * D].reshape(num_results, R, n, D)), sq(k[..., n * D:n * D + D]), \
+            sq(k[..., n * D + D:])
+        kernel_results = {"accept_prob": sq(out["accept_prob"].cpu().numpy()),
+                          "target_log_prob": sq(out["lp"].cpu().numpy()),
+                          "leapfrogs_taken": sq(out["n_leapfrog"].cpu().numpy()),
+                          "has_divergence": sq(out["diverged"].cpu().numpy()),
+                          "burnin_accept_prob": sq(burn["accept_prob"].cpu().numpy()),
+                          "burnin_leapfrogs_taken": sq(burn["n_leapfrog"].cpu().numpy()),
+                          "step_size": e.cpu().numpy(), "sampler": "nuts"}
+        return {"phi1s": self.phi1s, "phi2s": self.phi2s, "Xhat_init": self.Xhat_init,
+                "sigma_sqs_init": self.sigma_sqs_init, "thetas_init": self.thetas_init, "I": self.I,
+                "X_samps": X_pre, "sigma_sqs_samps": np.log(np.exp(s_pre) + 1.0) + sigma_sqs_LB,        # :418
+                "thetas_samps": np.log(np.exp(t_pre) + 1.0),                                             # :419
+                "kernel_results": kernel_results, "sample_results": [X_pre, s_pre, t_pre],
                 "minutes_elapsed": minutes}
 
     # ------------------------------------------------------------------------------------------

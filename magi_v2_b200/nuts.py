@@ -1,0 +1,275 @@
+"""Batched No-U-Turn sampler on top of the device log-posterior + gradient operator.
+
+The reference samples with ``tfp.mcmc.NoUTurnSampler(step_size=0.1)`` inside
+``DualAveragingStepSizeAdaptation(target_accept_prob=0.75, num_adaptation_steps=0.8 * burn-in)`` inside its own
+``LogAnnealedNUTS`` wrapper (magi_v2.py:357-371, :838-889), and hands NUTS one callable:
+``target_log_prob_fn(X, sigma_sqs_pre, thetas_pre)`` (:361-364, :866-869) whose value and gradient TFP asks for once per
+leapfrog step.  That callable is the drop-in boundary: here it is ``PosteriorProblem.logpost_grad`` (one launch of the
+fused CUDA kernel for ALL chains of ALL datasets), and this module is the tree-building around it -- the batched,
+iterative formulation TFP itself uses (all chains advance in lock-step, finished chains are masked, the U-turn checks
+of the dyadic sub-trees use a checkpoint memory of max_tree_depth momenta and momentum sums instead of recursion).
+
+Algorithm (restated from the published one; tensorflow-probability==0.24.0 is not installable here): multinomial
+NUTS with the generalised U-turn criterion -- leaves weighted by exp(H0 - H); uniform progressive sampling inside a
+new subtree; biased progressive sampling between the old tree and a completed subtree; a subtree that turns or
+diverges (H - H0 > max_energy_diff = 1000) is discarded and ends the transition; max_tree_depth = 10; the adaptation
+statistic is the mean of min(1, exp(H0 - H)) over every leaf evaluated.  Randomness is the sampler's counter-based
+Philox stream (csrc/rng.cuh), here evaluated with integer tensor arithmetic, so a transition can be checked draw for
+draw against the recursive single-chain oracle.
+
+Everything in this file is tensor bookkeeping on whatever device the state lives on; the arithmetic that costs
+anything is inside ``value_and_grad``.  `MAGI_v2.predict(sampler="nuts")` wires that to the CUDA operator only."""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+
+Tensor = torch.Tensor
+
+RNG_MOMENTUM, RNG_NUTS_DEPTH, RNG_NUTS_LEAF = 0, 2, 3
+_M32 = 0xFFFFFFFF
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Philox4x32-10 with int64 tensors holding uint32 values (same stream as csrc/rng.cuh)
+# ------------------------------------------------------------------------------------------------------------------
+def philox4x32_10(c0: Tensor, c1: Tensor, c2: Tensor, c3: Tensor, seed: int):
+    """Counters c0..c3: int64 tensors (broadcastable) with values in [0, 2^32).  Returns four int64 tensors."""
+    k0, k1 = seed & _M32, (seed >> 32) & _M32
+    c0, c1, c2, c3 = torch.broadcast_tensors(c0, c1, c2, c3)
+    for _ in range(10):
+        # 32 x 32 -> 64-bit products; split the multiplier so that nothing exceeds the signed 64-bit range
+        hi0, lo0 = _mulhilo(0xD2511F53, c0)
+        hi1, lo1 = _mulhilo(0xCD9E8D57, c2)
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = (k0 + 0x9E3779B9) & _M32
+        k1 = (k1 + 0xBB67AE85) & _M32
+    return c0, c1, c2, c3
+
+
+def _mulhilo(a: int, b: Tensor):
+    """(high, low) 32-bit halves of a * b for a < 2^32, 0 <= b < 2^32, using signed 64-bit arithmetic."""
+    a_hi, a_lo = a >> 16, a & 0xFFFF
+    t_lo = a_lo * b                                   # < 2^48
+    t_hi = a_hi * b                                   # < 2^48, weight 2^16
+    s = t_lo + ((t_hi & 0xFFFF) << 16)                # < 2^49
+    lo = s & _M32
+    hi = (t_hi >> 16) + (s >> 32)
+    return hi, lo
+
+
+def _u53(hi: Tensor, lo: Tensor) -> Tensor:
+    k = (hi << 21) ^ (lo >> 11)
+    return (k.to(torch.float64) + 0.5) * (2.0 ** -53)
+
+
+def rng_normals(seed: int, chain_ids: Tensor, iteration: int, count: int) -> Tensor:
+    """[C, count] standard normals: pair j of chain c -> Philox(ctr = (j, c, iteration, 0)) -> Box-Muller."""
+    npair = (count + 1) // 2
+    dev = chain_ids.device
+    j = torch.arange(npair, dtype=torch.int64, device=dev)[None, :]
+    it = torch.full((1, 1), int(iteration), dtype=torch.int64, device=dev)
+    r = philox4x32_10(j, chain_ids[:, None], it, torch.full_like(it, RNG_MOMENTUM), seed)
+    u1, u2 = _u53(r[0], r[1]), _u53(r[2], r[3])
+    rad = torch.sqrt(-2.0 * torch.log(u1))
+    ang = 2.0 * math.pi * u2
+    z = torch.stack([rad * torch.cos(ang), rad * torch.sin(ang)], dim=2).reshape(chain_ids.shape[0], 2 * npair)
+    return z[:, :count].contiguous()
+
+
+def rng_uniform_pairs(seed: int, chain_ids: Tensor, iteration: int, purpose: int, index0: int, count: int):
+    """Two [C, count] uniform arrays for counters (index0 + k, chain, iteration, purpose), k < count."""
+    dev = chain_ids.device
+    k = torch.arange(index0, index0 + count, dtype=torch.int64, device=dev)[None, :]
+    it = torch.full((1, 1), int(iteration), dtype=torch.int64, device=dev)
+    r = philox4x32_10(k, chain_ids[:, None], it, torch.full_like(it, int(purpose)), seed)
+    return _u53(r[0], r[1]), _u53(r[2], r[3])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# one transition for C chains
+# ------------------------------------------------------------------------------------------------------------------
+def _dot(a: Tensor, b: Tensor) -> Tensor:
+    return torch.einsum("cs,cs->c", a, b)
+
+
+def _sel(mask: Tensor, new: Tensor, old: Tensor) -> Tensor:
+    """In-place old <- where(mask, new, old) for [C, S] (or [C]) tensors; returns old."""
+    m = mask if old.dim() == 1 else mask[:, None]
+    return old.copy_(torch.where(m, new, old))
+
+
+def nuts_transition(z: Tensor, eps: Tensor, value_and_grad: Callable[[Tensor], Tuple[Tensor, Tensor]], seed: int,
+                    chain_ids: Tensor, iteration: int, max_tree_depth: int = 10, max_energy_diff: float = 1000.0,
+                    sync_every: int = 8) -> Dict[str, Tensor]:
+    """z [C, S] (updated in place to the selected proposals), eps [C] step sizes, value_and_grad(z) -> (lp [C], g [C, S]).
+    Returns accept_stat [C], n_leapfrog [C] (leaves evaluated while the chain was still building), depth [C],
+    diverged [C], lp [C] (log-posterior of the new state)."""
+    C, S = z.shape
+    dev, f64 = z.device, torch.float64
+    lp0, g0 = value_and_grad(z)
+    lp0, g0 = lp0.clone(), g0.clone()
+    p0 = rng_normals(seed, chain_ids, iteration, S)
+    H0 = -lp0 + 0.5 * _dot(p0, p0)
+    u_dir, u_acc = rng_uniform_pairs(seed, chain_ids, iteration, RNG_NUTS_DEPTH, 0, max_tree_depth)
+
+    zl, pl, gl = z.clone(), p0.clone(), g0.clone()           # leftmost / rightmost states of the tree
+    zr, pr, gr = z.clone(), p0.clone(), g0.clone()
+    rho = p0.clone()
+    logw = torch.zeros(C, dtype=f64, device=dev)
+    prop_z, prop_lp = z.clone(), lp0.clone()
+    sum_acc = torch.zeros(C, dtype=f64, device=dev)
+    n_leaf = torch.zeros(C, dtype=torch.int64, device=dev)
+    depth_out = torch.zeros(C, dtype=torch.int64, device=dev)
+    diverged = torch.zeros(C, dtype=torch.bool, device=dev)
+    active = torch.ones(C, dtype=torch.bool, device=dev)       # still doubling
+    ninf = torch.full((C,), -math.inf, dtype=f64, device=dev)
+    # checkpoint memory: slot popcount(i) holds, for the even leaf i, its momentum and the momentum sum before it
+    ck_p = [torch.empty_like(z) for _ in range(max(max_tree_depth - 1, 1))]
+    ck_rho = [torch.empty_like(z) for _ in range(max(max_tree_depth - 1, 1))]
+
+    for j in range(max_tree_depth):
+        if not bool(active.any()):
+            break
+        depth_out += active.to(torch.int64)
+        fwd = u_dir[:, j] < 0.5
+        e = torch.where(fwd, eps, -eps)
+        # the subtree starts from the end the direction points to
+        fm = fwd[:, None]
+        zc, pc, gc = torch.where(fm, zr, zl), torch.where(fm, pr, pl), torch.where(fm, gr, gl)
+        rho_sub = torch.zeros_like(z)
+        logw_sub = ninf.clone()
+        sub_z, sub_lp = zc.clone(), lp0.clone()
+        building = active.clone()                               # this subtree is still being built and is valid
+        n_sub = 1 << j
+        u_leaf, _ = rng_uniform_pairs(seed, chain_ids, iteration, RNG_NUTS_LEAF, n_sub - 1, n_sub)
+        log_u_leaf = torch.log(u_leaf)
+        for i in range(n_sub):
+            if i % sync_every == 0 and i > 0 and not bool(building.any()):
+                break
+            even = i % 2 == 0 and n_sub > 1
+            if even:
+                # an even leaf opens dyadic blocks: remember the momentum sum before it ...
+                slot = bin(i).count("1")
+                ck_rho[slot].copy_(rho_sub)
+            # one leapfrog step (TFP SimpleLeapfrogIntegrator, identity mass) with the signed step size
+            ph = pc + (0.5 * e)[:, None] * gc
+            zn = zc + e[:, None] * ph
+            lpn, gn = value_and_grad(zn)
+            pn = ph + (0.5 * e)[:, None] * gn
+            if even:
+                ck_p[slot].copy_(pn)                             # ... and its own momentum (the block's first)
+            dE = -lpn + 0.5 * _dot(pn, pn) - H0
+            dE = torch.where(torch.isfinite(dE), dE, torch.full_like(dE, math.inf))
+            sum_acc += torch.where(building, torch.exp(torch.clamp(-dE, max=0.0)), torch.zeros_like(dE))
+            n_leaf += building.to(torch.int64)
+            div = dE > max_energy_diff
+            diverged |= building & div
+            lw_new = torch.logaddexp(logw_sub, -dE)
+            take = building & (log_u_leaf[:, i] < (-dE - lw_new))
+            _sel(take, zn, sub_z)
+            _sel(take, lpn, sub_lp)
+            _sel(building, lw_new, logw_sub)
+            rho_sub = rho_sub + torch.where(building[:, None], pn, torch.zeros_like(pn))
+            _sel(building, zn, zc); _sel(building, pn, pc); _sel(building, gn, gc)
+            ok = ~div
+            if i % 2 == 1:
+                # dyadic blocks [i - 2^k + 1, i] that end here, k = 1 .. number of trailing ones of i
+                t = (~i & (i + 1)).bit_length() - 1
+                for k in range(1, t + 1):
+                    s = i - (1 << k) + 1
+                    slot = bin(s).count("1")
+                    rb = rho_sub - ck_rho[slot]
+                    ok = ok & (_dot(rb, ck_p[slot]) > 0.0) & (_dot(rb, pn) > 0.0)
+            building = building & ok
+        # merge the completed subtrees
+        done = building
+        swap = done & (torch.log(u_acc[:, j]) < (logw_sub - logw))
+        _sel(swap, sub_z, prop_z)
+        _sel(swap, sub_lp, prop_lp)
+        _sel(done, torch.logaddexp(logw, logw_sub), logw)
+        rho = rho + torch.where(done[:, None], rho_sub, torch.zeros_like(rho_sub))
+        mr, ml = done & fwd, done & ~fwd
+        _sel(mr, zc, zr); _sel(mr, pc, pr); _sel(mr, gc, gr)
+        _sel(ml, zc, zl); _sel(ml, pc, pl); _sel(ml, gc, gl)
+        no_turn = (_dot(rho, pl) > 0.0) & (_dot(rho, pr) > 0.0)
+        active = done & no_turn
+    z.copy_(prop_z)
+    acc = sum_acc / torch.clamp(n_leaf, min=1).to(f64)
+    return {"accept_stat": acc, "n_leapfrog": n_leaf, "depth": depth_out, "diverged": diverged, "lp": prop_lp}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# dual averaging (tfp.mcmc.DualAveragingStepSizeAdaptation, per chain) -- same recursion as the fused HMC kernel
+# (csrc/sampler.cu) and oracle.dual_averaging_update; da_state [C, 4] = (error_sum, log_averaging_step,
+# log_shrinkage_target, step)
+# ------------------------------------------------------------------------------------------------------------------
+def dual_averaging_update_(eps: Tensor, da: Tensor, accept: Tensor, num_adapt: int, target: float = 0.75,
+                           shrinkage: float = 0.05, smoothing: float = 10.0, decay: float = 0.75) -> None:
+    step = da[:, 3]
+    adapting = step < num_adapt
+    err = da[:, 0] + (target - accept)
+    t = step + 1.0
+    log_x = da[:, 2] - torch.sqrt(t) * err / (shrinkage * (t + smoothing))
+    eta = t ** (-decay)
+    lavg = eta * log_x + (1.0 - eta) * da[:, 1]
+    last = (step + 1.0) == num_adapt
+    new_eps = torch.where(last, torch.exp(lavg), torch.exp(log_x))
+    da[:, 0] = torch.where(adapting, err, da[:, 0])
+    da[:, 1] = torch.where(adapting, lavg, da[:, 1])
+    eps.copy_(torch.where(adapting, new_eps, eps))
+    da[:, 3] = step + 1.0
+
+
+def nuts_run_(z: Tensor, eps: Tensor, da: Tensor, value_and_grad_at: Callable[[Tensor, float], Tuple[Tensor, Tensor]],
+              *, n_iter: int, iter0: int = 0, num_adapt: int = 0, min_temp: float = 0.1,
+              fixed_beta_temp: Optional[float] = None, target_accept: float = 0.75, seed: int = 0,
+              chain_ids: Optional[Tensor] = None, max_tree_depth: int = 10,
+              on_sample: Optional[Callable[[int, Tensor, Dict[str, Tensor]], None]] = None) -> Dict[str, Tensor]:
+    """n_iter NUTS transitions in place on z [C, S], eps [C], da [C, 4].  value_and_grad_at(z, beta_temp) evaluates
+    the tempered log-posterior (magi_v2.py:348) at temperature beta_temp = max(1 / log(step + 2), min_temp)
+    (:833-835, :855) of the global iteration.  `on_sample(it, z, info)` is called after every transition."""
+    C = z.shape[0]
+    if chain_ids is None:
+        chain_ids = torch.arange(C, dtype=torch.int64, device=z.device)
+    acc = torch.empty((n_iter, C), dtype=torch.float64, device=z.device)
+    nleap = torch.empty((n_iter, C), dtype=torch.int64, device=z.device)
+    lps = torch.empty((n_iter, C), dtype=torch.float64, device=z.device)
+    div = torch.zeros((n_iter, C), dtype=torch.bool, device=z.device)
+    for it in range(n_iter):
+        g_it = iter0 + it
+        bt = float(fixed_beta_temp) if fixed_beta_temp else max(1.0 / math.log(g_it + 2.0), min_temp)
+        info = nuts_transition(z, eps, lambda zz: value_and_grad_at(zz, bt), seed, chain_ids, g_it, max_tree_depth)
+        dual_averaging_update_(eps, da, info["accept_stat"], num_adapt, target_accept)
+        acc[it], nleap[it], lps[it], div[it] = info["accept_stat"], info["n_leapfrog"], info["lp"], info["diverged"]
+        if on_sample is not None:
+            on_sample(it, z, info)
+    return {"accept_prob": acc, "n_leapfrog": nleap, "lp": lps, "diverged": div}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the product wiring: state = [X | sigma_sqs_pre | thetas_pre] per chain, target = the CUDA operator
+# ------------------------------------------------------------------------------------------------------------------
+def problem_value_and_grad(prob, R: int) -> Callable[[Tensor, float], Tuple[Tensor, Tensor]]:
+    """value_and_grad_at(z [B*R, S], beta_temp) for an `ops.PosteriorProblem`: splits the packed state into the three
+    state parts of magi_v2.py:383, calls `magi_b200_logpost_grad` (CUDA; raises without it) and re-packs the gradient."""
+    B, n, D, P = prob.B, prob.n, prob.D, prob.P
+    nD = n * D
+
+    def value_and_grad_at(z: Tensor, beta_temp: float):
+        X = z[:, :nD].reshape(B, R, n, D).contiguous()
+        s = z[:, nD:nD + D].reshape(B, R, D).contiguous()
+        tau = z[:, nD + D:].reshape(B, R, P).contiguous()
+        bt = torch.full((B, R), float(beta_temp), dtype=torch.float64, device=z.device)
+        lp, gX, gs, gt = prob.logpost_grad(X, s, tau, bt)
+        return lp.reshape(B * R), torch.cat([gX.reshape(B * R, nD), gs.reshape(B * R, D), gt.reshape(B * R, P)], dim=1)
+
+    return value_and_grad_at
+
+
+def pack_state(X: Tensor, s: Tensor, tau: Tensor) -> Tensor:
+    """[B,R,n,D], [B,R,D], [B,R,P] -> z [B*R, n*D + D + P]."""
+    B, R = X.shape[:2]
+    return torch.cat([X.reshape(B * R, -1), s.reshape(B * R, -1), tau.reshape(B * R, -1)], dim=1).contiguous()

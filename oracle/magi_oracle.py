@@ -610,3 +610,147 @@ def hmc_chain(c: PosteriorConstants, model: str, z0, n_iter, n_leapfrog, eps0, s
         out_z.append(z.copy()); out_acc.append(acc_prob); out_eps.append(eps)
         out_lp.append(lp1 if accepted else lp0)
     return np.array(out_z), np.array(out_acc), np.array(out_eps), np.array(out_lp)
+
+
+# ---- NUTS -------------------------------------------------------
+# tfp.mcmc.NoUTurnSampler (tensorflow-probability==0.24.0, mcmc/nuts.py; source not under
+# /root/reference -- call sites magi_v2.py:360-366, :866-869) restated from the published algorithm
+# (Hoffman & Gelman 2014 with Betancourt's multinomial sampling and the generalised U-turn
+# criterion, which is what TFP implements): tree doubling up to max_tree_depth = 10, leaves weighted
+# by exp(H0 - H), uniform progressive sampling inside a new subtree, biased progressive sampling
+# between the old tree and the new subtree, U-turn checked on every complete dyadic sub-tree of the
+# new subtree and on the merged tree with rho = sum of momenta, divergence when H - H0 > 1000.
+# This version is RECURSIVE (one chain); the product (magi_v2_b200/nuts.py) is the iterative batched
+# form with checkpoint memory -- the two are checked against each other draw for draw.
+
+RNG_PURPOSE_NUTS_DEPTH = 2     # per doubling: word pair 0 -> direction, pair 1 -> subtree acceptance
+RNG_PURPOSE_NUTS_LEAF = 3      # per leaf: multinomial selection inside the new subtree
+
+
+def rng_uniform_pair(seed: int, chain_id: int, iteration: int, purpose: int, index: int):
+    ctr = np.array([[index, chain_id, iteration, purpose]], dtype=np.uint32)
+    key = np.array([[seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF]], dtype=np.uint32)
+    r = philox4x32_10(ctr, key)
+    return float(_u53(r[:, 0], r[:, 1])[0]), float(_u53(r[:, 2], r[:, 3])[0])
+
+
+def _logaddexp(a, b):
+    return float(np.logaddexp(a, b))
+
+
+def _no_uturn(rho, p_first, p_last):
+    return (np.dot(rho, p_first) > 0.0) and (np.dot(rho, p_last) > 0.0)
+
+
+def nuts_transition(z, eps, value_and_grad, seed, chain_id, iteration, max_tree_depth=10,
+                    max_energy_diff=1000.0):
+    """One NUTS transition from z.  Returns (z_new, lp_new, accept_stat, n_leapfrog, depth, diverged)."""
+    S = len(z)
+    lp0, g0 = value_and_grad(z)
+    p0 = rng_normals(seed, chain_id, iteration, S)
+    H0 = -lp0 + 0.5 * np.dot(p0, p0)
+    stats = {"sum_acc": 0.0, "n_leaf": 0, "leaf_index": 0, "diverged": False}
+
+    def build(zc, pc, gc, direction, depth):
+        """2^depth leaves continuing from (zc, pc, gc).  Returns dict with the last state, rho, first / last
+        momentum, log weight, proposal and `ok` (False = turning or diverged: nothing after it is built)."""
+        if depth == 0:
+            e = direction * eps
+            ph = pc + 0.5 * e * gc
+            zn = zc + e * ph
+            lpn, gn = value_and_grad(zn)
+            pn = ph + 0.5 * e * gn
+            H = -lpn + 0.5 * np.dot(pn, pn)
+            dE = H - H0
+            if not np.isfinite(dE):
+                dE = np.inf
+            stats["sum_acc"] += min(1.0, math.exp(min(0.0, -dE)))
+            stats["n_leaf"] += 1
+            u_leaf, _ = rng_uniform_pair(seed, chain_id, iteration, RNG_PURPOSE_NUTS_LEAF, stats["leaf_index"])
+            stats["leaf_index"] += 1
+            div = dE > max_energy_diff
+            stats["diverged"] |= bool(div)
+            return {"z": zn, "p": pn, "g": gn, "rho": pn.copy(), "p_first": pn, "p_last": pn, "logw": -dE,
+                    "prop": (zn, lpn), "ok": not div, "u": [u_leaf]}
+        a = build(zc, pc, gc, direction, depth - 1)
+        if not a["ok"]:
+            return a
+        b = build(a["z"], a["p"], a["g"], direction, depth - 1)
+        logw = _logaddexp(a["logw"], b["logw"])
+        out = dict(b)
+        out["rho"] = a["rho"] + b["rho"]
+        out["p_first"] = a["p_first"]
+        out["logw"] = logw
+        out["u"] = a["u"] + b["u"]
+        out["prop"] = a["prop"]          # resolved below (sequential selection, leaf by leaf)
+        out["ok"] = b["ok"] and _no_uturn(out["rho"], out["p_first"], out["p_last"])
+        out["halves"] = (a, b)
+        return out
+
+    def leaves(t):
+        if "halves" not in t:
+            return [t]
+        a, b = t["halves"]
+        return leaves(a) + leaves(b)
+
+    z_l = z_r = np.array(z, dtype=np.float64)
+    p_l = p_r = p0
+    g_l = g_r = g0
+    rho = p0.copy()
+    logw = 0.0
+    prop_z, prop_lp = np.array(z, dtype=np.float64), lp0
+    depth = 0
+    while depth < max_tree_depth:
+        u_dir, u_acc = rng_uniform_pair(seed, chain_id, iteration, RNG_PURPOSE_NUTS_DEPTH, depth)
+        direction = 1.0 if u_dir < 0.5 else -1.0
+        if direction > 0:
+            t = build(z_r, p_r, g_r, direction, depth)
+        else:
+            t = build(z_l, p_l, g_l, direction, depth)
+        depth += 1
+        if not t["ok"]:
+            break
+        # uniform progressive selection inside the subtree, leaf by leaf: leaf i replaces the running
+        # proposal with probability w_i / (w_0 + ... + w_i)
+        run_w, sub_prop = -np.inf, None
+        for lf in leaves(t):
+            run_w = _logaddexp(run_w, lf["logw"])
+            if math.log(lf["u"][0]) < lf["logw"] - run_w:
+                sub_prop = lf["prop"]
+        if math.log(u_acc) < t["logw"] - logw:
+            prop_z, prop_lp = sub_prop
+        logw = _logaddexp(logw, t["logw"])
+        rho = rho + t["rho"]
+        if direction > 0:
+            z_r, p_r, g_r = t["z"], t["p"], t["g"]
+        else:
+            z_l, p_l, g_l = t["z"], t["p"], t["g"]
+        if not _no_uturn(rho, p_l, p_r):
+            break
+    acc = stats["sum_acc"] / max(stats["n_leaf"], 1)
+    return prop_z, prop_lp, acc, stats["n_leaf"], depth, stats["diverged"]
+
+
+def nuts_chain(c: PosteriorConstants, model: str, z0, n_iter, eps0, seed, chain_id, num_adaptation_steps=0,
+               min_temp=0.1, step0=0, fixed_beta_temp=None, max_tree_depth=10):
+    """The reference's sampler stack (magi_v2.py:357-371, :852-879): NUTS(step 0.1) inside dual averaging
+    (target 0.75, 0.8 * burn-in adaptation steps) inside the log-annealing wrapper."""
+    n, D = c.n, c.D
+    P = len(z0) - n * D - D
+    da = DualAveragingState.create(eps0)
+    z = np.array(z0, dtype=np.float64, copy=True)
+    out_z, out_acc, out_eps, out_nleap = [], [], [], []
+    for it in range(n_iter):
+        bt = float(fixed_beta_temp) if fixed_beta_temp is not None else \
+            float(logarithmic_temperature_schedule(step0 + it, min_temp))
+
+        def vg(zz):
+            X, s, tau = unpack_state(zz, n, D, P)
+            lp, gX, gs, gt = log_posterior_and_grad_analytic(X, s, tau, bt, c, model)
+            return lp, pack_state(gX, gs, gt)
+
+        eps = da.step_size
+        z, _, acc, nl, _, _ = nuts_transition(z, eps, vg, seed, chain_id, step0 + it, max_tree_depth)
+        da = dual_averaging_update(da, acc, num_adaptation_steps)
+        out_z.append(z.copy()); out_acc.append(acc); out_eps.append(eps); out_nleap.append(nl)
+    return np.array(out_z), np.array(out_acc), np.array(out_eps), np.array(out_nleap)
