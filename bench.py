@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--hmc-iters", type=int, default=4, help="HMC transitions per timed HMC step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hmc", action="store_true")
+    ap.add_argument("--no-nuts", action="store_true")
+    ap.add_argument("--nuts-depth", type=int, default=4, help="max_tree_depth of the timed NUTS transitions")
     ap.add_argument("--cpu-evals-per-worker", type=int, default=24)
     return ap.parse_args()
 
@@ -324,6 +326,43 @@ def run_b200(args):
                "e2e_samples_per_s": samples / (ms_hmc_e2e * 1e-3), "ms_per_launch": ms_hmc / hsteps,
                "accept_rate_note": "step size 2e-4, fixed beta_temp 0.37, no adaptation"}
 
+    # -- (4) NUTS (the reference's sampler): tree building in nuts.py, one logpost_grad launch per leapfrog --------
+    nuts_res = None
+    if not args.no_nuts:
+        from magi_v2_b200 import nuts
+        zN = nuts.pack_state(X, s, tau)
+        epsN = torch.full((B * R,), 2e-4, dtype=torch.float64, device=dev)
+        daN = torch.zeros((B * R, 4), dtype=torch.float64, device=dev)
+        ids = torch.arange(rank * B * R, (rank + 1) * B * R, dtype=torch.int64, device=dev)
+        vg = nuts.problem_value_and_grad(prob, R)
+        itn, leaves, launches = [0], [0], [0]
+
+        def counted_vg(zz, bt_):
+            launches[0] += 1
+            return vg(zz, bt_)
+
+        def nuts_step():
+            o = nuts.nuts_run_(zN, epsN, daN, counted_vg, n_iter=1, iter0=itn[0], num_adapt=0, fixed_beta_temp=0.37,
+                               seed=1 + rank, chain_ids=ids, max_tree_depth=args.nuts_depth)
+            itn[0] += 1
+            leaves[0] += int(o["n_leapfrog"].sum())
+
+        nuts_step()
+        leaves[0], launches[0] = 0, 0
+        nsteps = 2
+        ms_nuts = timed(nuts_step, nsteps, 1)
+        launches_timed = launches[0] * nsteps // (nsteps + 1)
+        tot = torch.tensor([leaves[0] * nsteps / (nsteps + 1.0)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot)
+        nuts_res = {"transitions_per_s": B * R * world * nsteps / (ms_nuts * 1e-3), "max_tree_depth": args.nuts_depth,
+                    "leapfrogs_per_s": float(tot.item()) / (ms_nuts * 1e-3),
+                    "mean_leapfrogs_per_transition": float(tot.item()) / (B * R * world * nsteps),
+                    "ms_per_lockstep_leapfrog": ms_nuts / max(launches_timed, 1),
+                    "note": "step size 2e-4, fixed beta_temp 0.37; every chain of every dataset advances in lock-step, "
+                            "one magi_b200_logpost_grad launch per leapfrog + tensor bookkeeping"}
+        del zN
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -375,7 +414,7 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": args.steps, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "hmc": hmc, "setup_s": t_setup}
+            "hmc": hmc, "nuts": nuts_res, "setup_s": t_setup}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -101,10 +101,11 @@ class MagiBatch:
 
     def predict(self, num_results: int = 1000, num_burnin_steps: int = 1000, n_chains: int = 8,
                 n_leapfrog: int = 32, seed: int = 0, step_size: float = 0.1, keep_X_mean: bool = True,
-                gather: bool = True):
+                gather: bool = True, sampler: str = "hmc", max_tree_depth: int = 10):
         """magi_v2.py:286-425 for every dataset: returns thetas_samps [B, n_chains, num_results, P],
         sigma_sqs_samps [B, n_chains, num_results, D] (all datasets of all ranks when `gather`), the
-        posterior mean / sd of the local trajectories and per-chain acceptance / step sizes."""
+        posterior mean / sd of the local trajectories and per-chain acceptance / step sizes.  sampler = "hmc"
+        runs whole chains inside the fused kernel; "nuts" is the reference's sampler (`nuts.py`)."""
         import torch
         if self.prob is None:
             raise RuntimeError("call initial_fit() first")
@@ -122,6 +123,9 @@ class MagiBatch:
         da[..., 2] = float(np.log(10.0 * step_size))
         num_adapt = int(0.8 * num_burnin_steps)                                                     # :365
         cid0 = self.lo * R                                      # global chain ids: results independent of sharding
+        if sampler == "nuts":
+            return self._predict_nuts(X, s, tau, eps, da, num_results, num_burnin_steps, num_adapt, seed, cid0,
+                                      max_tree_depth, keep_X_mean, gather)
         burn = self.prob.hmc_run_(X, s, tau, eps, da, n_iter=num_burnin_steps, n_leapfrog=n_leapfrog, iter0=0,
                                   num_adapt=num_adapt, seed=seed, chain_id0=cid0, keep_theta=False, keep_sigma=False)
         Xsum = torch.zeros((B, R, n, D), dtype=torch.float64, device=dev) if keep_X_mean else None
@@ -143,4 +147,48 @@ class MagiBatch:
             mean = Xsum.sum(dim=1) / (R * num_results)
             var = Xsq.sum(dim=1) / (R * num_results) - mean ** 2
             res["X_mean"], res["X_sd"] = mean.cpu().numpy(), var.clamp_min(0).sqrt().cpu().numpy()
+        return res
+
+    def _predict_nuts(self, X, s, tau, eps, da, num_results, num_burnin_steps, num_adapt, seed, cid0, max_tree_depth,
+                      keep_X_mean, gather):
+        import torch
+        from . import nuts
+        B, R, D, P, n = self.B, X.shape[1], self.model.D, self.model.P, len(self.I)
+        z = nuts.pack_state(X, s, tau)
+        e, d = eps.reshape(-1), da.reshape(-1, 4)
+        ids = torch.arange(cid0, cid0 + B * R, dtype=torch.int64, device=z.device)
+        vg = nuts.problem_value_and_grad(self.prob, R)
+        LB = torch.as_tensor(self.sigma_sqs_LB, dtype=torch.float64, device=z.device)[:, None]
+        burn = nuts.nuts_run_(z, e, d, vg, n_iter=num_burnin_steps, num_adapt=num_adapt, seed=seed, chain_ids=ids,
+                              max_tree_depth=max_tree_depth)
+        th = torch.empty((num_results, B, R, P), dtype=torch.float64, device=z.device)
+        sg = torch.empty((num_results, B, R, D), dtype=torch.float64, device=z.device)
+        Xsum = torch.zeros((B, R, n * D), dtype=torch.float64, device=z.device)
+        Xsq = torch.zeros_like(Xsum)
+
+        def on_sample(it, zz, info):
+            zz = zz.view(B, R, -1)
+            th[it] = torch.nn.functional.softplus(zz[..., n * D + D:])                            # :419
+            sg[it] = torch.nn.functional.softplus(zz[..., n * D:n * D + D]) + LB                  # :418
+            if keep_X_mean:
+                Xsum.add_(zz[..., :n * D]); Xsq.addcmul_(zz[..., :n * D], zz[..., :n * D])
+
+        out = nuts.nuts_run_(z, e, d, vg, n_iter=num_results, iter0=num_burnin_steps, num_adapt=num_adapt, seed=seed,
+                             chain_ids=ids, max_tree_depth=max_tree_depth, on_sample=on_sample)
+        if gather and self.world > 1:
+            sizes = parallel.shard_sizes(self.B_total, self.world)
+            th = parallel.gather_samples(th, dataset_dim=1, sizes=sizes)
+            sg = parallel.gather_samples(sg, dataset_dim=1, sizes=sizes)
+        res = {"thetas_samps": th.permute(1, 2, 0, 3).cpu().numpy(), "sigma_sqs_samps": sg.permute(1, 2, 0, 3).cpu().numpy(),
+               "accept_prob": out["accept_prob"].mean(dim=0).view(B, R).cpu().numpy(),
+               "leapfrogs_taken": out["n_leapfrog"].view(-1, B, R).cpu().numpy(),
+               "step_size": e.view(B, R).cpu().numpy(),
+               "burnin_accept_prob": burn["accept_prob"].mean(dim=0).view(B, R).cpu().numpy(),
+               "phi1s": self.phi1s, "phi2s": self.phi2s, "thetas_init": self.thetas_init, "I": self.I,
+               "dataset_range": (self.lo, self.hi)}
+        if keep_X_mean:
+            mean = Xsum.sum(dim=1) / (R * num_results)
+            var = Xsq.sum(dim=1) / (R * num_results) - mean ** 2
+            res["X_mean"] = mean.view(B, n, D).cpu().numpy()
+            res["X_sd"] = var.clamp_min(0).sqrt().view(B, n, D).cpu().numpy()
         return res

@@ -84,9 +84,10 @@ def batch_constants(ts_obs: np.ndarray, X_obs: np.ndarray, discretization: int):
 
 
 def device_problem(model: str, I, phi1, phi2, y, mask, N_ds, beta, mu, LB, bandsize, device, nu: float = 2.01,
-                   chunk: int = 512, uniform_grid: bool = True):
+                   chunk: int = 512, uniform_grid: bool = True, keep_matrices: bool = False):
     """Kernel matrices for all datasets on the device (in chunks to bound the transient memory) and
-    the PosteriorProblem that holds every constant of the log-posterior."""
+    the PosteriorProblem that holds every constant of the log-posterior.  `keep_matrices` also keeps the
+    dense banded m and K^-1 ([B,D,n,n] each, `prob.kept_matrices`) for the theta initialisation."""
     import torch
     from . import ops
     dev = torch.device(device)
@@ -97,7 +98,7 @@ def device_problem(model: str, I, phi1, phi2, y, mask, N_ds, beta, mu, LB, bands
     packed = torch.empty(B * D * 3 * npad * npad, dtype=torch.float64, device=dev)
     I_d, p1, p2 = T(I), T(phi1), T(phi2)
     band = -1 if bandsize is None else int(bandsize)
-    infos = []
+    infos, kept = [], []
     per = D * 3 * npad * npad
     for b0 in range(0, B, chunk):
         b1 = min(B, b0 + chunk)
@@ -105,10 +106,14 @@ def device_problem(model: str, I, phi1, phi2, y, mask, N_ds, beta, mu, LB, bands
         Cinv, m, Kinv, _, info = ops.factor_derive(C, Cp, Cpp, band, 0.0)
         packed[b0 * per:b1 * per] = ops.pack_matrices(Cinv, m, Kinv)
         infos.append(info)
+        if keep_matrices:
+            kept.append((m, Kinv))
         del C, Cp, Cpp, Cinv, m, Kinv
     info = torch.cat(infos)
     prob = ops.PosteriorProblem(model, packed, mu=T(mu), y=T(y), mask=T(mask, torch.uint8), N_ds=T(N_ds),
                                 beta=T(beta), LB=T(LB), n=n, band=bandsize)
+    if keep_matrices:
+        prob.kept_matrices = (torch.cat([k[0] for k in kept]), torch.cat([k[1] for k in kept]))
     return prob, info
 
 

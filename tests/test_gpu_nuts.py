@@ -84,3 +84,6 @@ def test_magi_batch_front_end(cuda_device):
     assert np.isfinite(res["thetas_samps"]).all() and np.all(res["thetas_samps"] > 0)
     assert res["X_mean"].shape == (20, 161, 4) and np.isfinite(res["X_sd"]).all()
     assert res["accept_prob"].mean() > 0.3
+    rn = mb.predict(num_results=10, num_burnin_steps=20, n_chains=2, seed=2, sampler="nuts", max_tree_depth=5)
+    assert rn["thetas_samps"].shape == (20, 2, 10, 3) and np.isfinite(rn["thetas_samps"]).all()
+    assert rn["leapfrogs_taken"].max() > 1 and rn["X_mean"].shape == (20, 161, 4)
