@@ -6,11 +6,10 @@ log-posterior + gradient, leapfrog/HMC) running as sm_100a CUDA kernels through 
 Differences from the reference, all stated in DESIGN.md:
   * ``f_vec`` must resolve to an ODE system compiled into the library (name, OdeModel, or a callable that
     matches one when probed with numpy inputs) -- see models.py;
-  * the sampler is fixed-length HMC with the reference's leapfrog, tempering schedule and dual-averaging
-    step-size adaptation (NUTS tree building is a "next" row); ``predict`` can run
-    many chains at once (``n_chains``) and is seedable;
+  * ``predict(sampler="nuts")`` is the reference's sampler stack (NUTS trees, dual averaging, log annealing; nuts.py);
+    the default ``sampler="hmc"`` is fixed-length HMC with the same leapfrog, tempering schedule and adaptation, run
+    entirely inside one fused kernel; ``predict`` can run many chains at once (``n_chains``) and is seedable;
   * C^-1 and K^-1 come from Cholesky factorisations instead of SVD pseudo-inverses;
-  * components that are never observed (magi_v2.py:182-268) are not supported yet.
 A CUDA device is required: there is no CPU fallback."""
 from __future__ import annotations
 
@@ -72,12 +71,10 @@ class MAGI_v2:
         self.factor_info = None
 
     # ------------------------------------------------------------------------------------------
-    def initial_fit(self, discretization: int, verbose=False, hparams: Optional[dict] = None):
-        """magi_v2.py:82-277.  ``hparams`` = {"phi1s", "phi2s", "sigma_sqs"} skips the GP
-        hyper-parameter fit (the reference lets the user overwrite the fitted values, :76-80)."""
-        if self.D_unobserved:
-            raise NotImplementedError("completely unobserved components (magi_v2.py:182-268) are outside "
-                                      "the scope of this build")
+    def initial_fit(self, discretization: int, verbose=False, hparams: Optional[dict] = None, seed=None):
+        """magi_v2.py:82-277.  ``hparams`` = {"phi1s", "phi2s", "sigma_sqs"} (observed components) skips their GP
+        hyper-parameter fit (the reference lets the user overwrite the fitted values, :76-80).  ``seed`` seeds the
+        random start of completely unobserved components (the reference draws it unseeded, :224-227)."""
         self.I, self.X_obs_discret = self._discretize(self.ts_obs, self.X_obs, discretization)      # :85
         self.mag_I = self.I.shape[0]
         self.beta = float((self.D * self.mag_I) / self.N_ds.sum())                                   # :89
@@ -93,10 +90,28 @@ class MAGI_v2:
         self.Xhat_init = self.X_obs_discret.copy()
         self.Xhat_init[:, self.observed_indicators] = self.X_interp_obs
         self.mu_ds[self.observed_indicators] = self.X_interp_obs.mean(axis=0)                        # :114
-        # kernel matrices on the device: replaces the per-component loop :122-128 and banding :271-274
-        self._device_kernel_matrices()
-        # theta initialisation (:132-179): Adam on the t2-only objective from theta = 1
-        self.thetas_init = self._fit_thetas_init()
+        if self.D_unobserved == 0:
+            # kernel matrices on the device: replaces the per-component loop :122-128 and banding :271-274
+            self._device_kernel_matrices()
+            # theta initialisation (:132-179): Adam on the t2-only objective from theta = 1
+            self.thetas_init = self._fit_thetas_init()
+        else:
+            # :182-268 -- (thetas_init, X_unobs) jointly by gradient matching, then the GP hyper-parameters of the
+            # unobserved components from the fitted trajectories, then every kernel matrix in one device call
+            from .init_fit import fit_unobserved
+            X_smoothed_obs = self.cv_cubic_smoother(self.I, self.X_interp_obs)                       # :192
+            self.X_interp_unobs, self.thetas_init, l0, l1 = fit_unobserved(
+                self.model, self.I, X_smoothed_obs, self.observed_components, self.unobserved_components,
+                self.X_interp_obs, num_iters=self.THETA_INIT_ITERS, lr=self.ADAM_LR, seed=seed)
+            if verbose:
+                print(f"Fitting X_unobs and theta: gradient-matching loss {l0:.4g} -> {l1:.4g}")
+            hp_u = self._fit_kernel_hparams(I=self.I, X_filled=self.X_interp_unobs, verbose=verbose)  # :253
+            self.phi1s[self.unobserved_components] = hp_u["phi1s"]
+            self.phi2s[self.unobserved_components] = hp_u["phi2s"]
+            self.sigma_sqs_init[self.unobserved_components] = hp_u["sigma_sqs"]
+            self.Xhat_init[:, self.unobserved_components] = self.X_interp_unobs
+            self.mu_ds[self.unobserved_components] = self.X_interp_unobs.mean(axis=0)                # :260
+            self._device_kernel_matrices()                                                           # :262-274
         self.Xhat_init = self.cv_cubic_smoother(self.I, self.Xhat_init)                              # :277
 
     def _device_kernel_matrices(self):

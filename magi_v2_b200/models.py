@@ -13,26 +13,42 @@ from typing import Callable, Dict, Union
 import numpy as np
 
 
+def _cat(cols, like):
+    """Column concatenation for numpy arrays or torch tensors (the latter only for the autograd-based
+    initialisation of unobserved components, init_fit.py)."""
+    if isinstance(like, np.ndarray):
+        return np.concatenate(cols, axis=1)
+    import torch
+    return torch.cat(cols, dim=1)
+
+
+def _roll(X, k):
+    if isinstance(X, np.ndarray):
+        return np.roll(X, k, axis=1)
+    import torch
+    return torch.roll(X, k, dims=1)
+
+
 def _seir3(t, X, th):
-    S = 1.0 - X.sum(axis=1, keepdims=True)
+    S = 1.0 - X.sum(1)[:, None]
     E, I = X[:, 0:1], X[:, 1:2]
-    return np.concatenate([th[0] * S * I - th[2] * E, th[2] * E - th[1] * I, th[1] * I], axis=1)
+    return _cat([th[0] * S * I - th[2] * E, th[2] * E - th[1] * I, th[1] * I], X)
 
 
 def _seir4(t, X, th):
     S, E, I = X[:, 0:1], X[:, 1:2], X[:, 2:3]
-    return np.concatenate([-th[0] * S * I, th[0] * S * I - th[2] * E, th[2] * E - th[1] * I, th[1] * I], axis=1)
+    return _cat([-th[0] * S * I, th[0] * S * I - th[2] * E, th[2] * E - th[1] * I, th[1] * I], X)
 
 
 def _sirw(t, X, th):
     S, I, R, W = X[:, 0:1], X[:, 1:2], X[:, 2:3], X[:, 3:4]
-    beta, phi, xi, chi, kappa = th
-    return np.concatenate([-beta * S * I + kappa * W, beta * S * I - phi * I, phi * I - xi * R + chi * I * W,
-                           xi * R - chi * I * W - kappa * W], axis=1)
+    beta, phi, xi, chi, kappa = th[0], th[1], th[2], th[3], th[4]
+    return _cat([-beta * S * I + kappa * W, beta * S * I - phi * I, phi * I - xi * R + chi * I * W,
+                 xi * R - chi * I * W - kappa * W], X)
 
 
 def _lorenz96(t, X, th):
-    return (np.roll(X, -1, axis=1) - np.roll(X, 2, axis=1)) * np.roll(X, 1, axis=1) - X + th[0]
+    return (_roll(X, -1) - _roll(X, 2)) * _roll(X, 1) - X + th[0]
 
 
 def _dtheta_fd(f):

@@ -92,3 +92,23 @@ def test_twenty_datasets_as_one_batch(cuda_device):
     # the alpha = 0.15 files (noise sd = 15 % of the range) are only required to stay finite and positive:
     # with 500 short transitions from a perturbed start their theta has not equilibrated
     assert np.all(mean > 0) and np.isfinite(mean).all()
+
+
+def test_completely_unobserved_component(cuda_device):
+    """magi_v2.py:182-268: S of the 4-component SEIR system is never observed; (theta, S) are initialised jointly by
+    gradient matching, S gets its own GP hyper-parameters and matrices, and the sampler runs on all four components."""
+    from magi_v2_b200 import MAGI_v2
+    g = load_golden("seir_datasets.npz")
+    X = g["X_obs"][0].copy()
+    X[X < 0.0] = 0.0
+    X[:, 0] = np.nan
+    model = MAGI_v2(D_thetas=3, ts_obs=g["ts_obs"], X_obs=X, bandsize=80, f_vec="seir4")
+    assert list(model.unobserved_components) == [0] and model.N_ds[0] == 0
+    model.THETA_INIT_ITERS = 3000
+    model.initial_fit(discretization=1, seed=0)
+    assert np.isfinite(model.Xhat_init).all() and np.isfinite(model.thetas_init).all()
+    assert np.all(np.isfinite(model.phi1s)) and np.all(model.phi2s > 0) and np.all(model.factor_info == 0)
+    res = model.predict(num_results=60, num_burnin_steps=60, n_chains=2, n_leapfrog=8, seed=3)
+    assert res["X_samps"].shape == (2, 60, 161, 4) and np.isfinite(res["X_samps"]).all()
+    assert np.isfinite(res["thetas_samps"]).all() and np.all(res["thetas_samps"] > 0)
+    assert np.all(res["sigma_sqs_samps"] > 0)
