@@ -334,24 +334,20 @@ def run_b200(args):
         epsN = torch.full((B * R,), 2e-4, dtype=torch.float64, device=dev)
         daN = torch.zeros((B * R, 4), dtype=torch.float64, device=dev)
         ids = torch.arange(rank * B * R, (rank + 1) * B * R, dtype=torch.int64, device=dev)
-        vg = nuts.problem_value_and_grad(prob, R)
-        itn, leaves, launches = [0], [0], [0]
-
-        def counted_vg(zz, bt_):
-            launches[0] += 1
-            return vg(zz, bt_)
+        eng = nuts.FusedLeafEngine(prob, R)
+        itn, leaves = [0], [0]
 
         def nuts_step():
-            o = nuts.nuts_run_(zN, epsN, daN, counted_vg, n_iter=1, iter0=itn[0], num_adapt=0, fixed_beta_temp=0.37,
-                               seed=1 + rank, chain_ids=ids, max_tree_depth=args.nuts_depth)
+            o = nuts.nuts_run_(zN, epsN, daN, None, n_iter=1, iter0=itn[0], num_adapt=0, fixed_beta_temp=0.37,
+                               seed=1 + rank, chain_ids=ids, max_tree_depth=args.nuts_depth, leaf_engine=eng)
             itn[0] += 1
             leaves[0] += int(o["n_leapfrog"].sum())
 
         nuts_step()
-        leaves[0], launches[0] = 0, 0
+        leaves[0] = 0
         nsteps = 2
         ms_nuts = timed(nuts_step, nsteps, 1)
-        launches_timed = launches[0] * nsteps // (nsteps + 1)
+        launches_timed = nsteps * (1 << args.nuts_depth)        # 2^depth - 1 leaves + the starting point
         tot = torch.tensor([leaves[0] * nsteps / (nsteps + 1.0)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tot)
@@ -360,7 +356,7 @@ def run_b200(args):
                     "mean_leapfrogs_per_transition": float(tot.item()) / (B * R * world * nsteps),
                     "ms_per_lockstep_leapfrog": ms_nuts / max(launches_timed, 1),
                     "note": "step size 2e-4, fixed beta_temp 0.37; every chain of every dataset advances in lock-step, "
-                            "one magi_b200_logpost_grad launch per leapfrog + tensor bookkeeping"}
+                            "per leaf: magi_b200_nuts_leaf_pre, magi_b200_logpost_grad, magi_b200_nuts_leaf_post"}
         del zN
 
     if rank != 0:

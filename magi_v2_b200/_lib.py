@@ -31,6 +31,13 @@ class HmcConfig(C.Structure):
                 ("target_accept", C.c_double), ("seed", C.c_uint64), ("chain_id0", C.c_uint32)]
 
 
+class NutsSubtree(C.Structure):
+    """magi_nuts_subtree_t (include/magi_b200_nuts.h)"""
+    _fields_ = [("C", C.c_int), ("nD", C.c_int), ("D", C.c_int), ("P", C.c_int)] + \
+               [(k, C.c_void_p) for k in ("zc", "pc", "gc", "rho_sub", "sub_z", "sub_lp", "logw_sub", "sum_acc", "n_leaf",
+                                          "building", "diverged", "ck_p", "ck_rho", "e", "H0")]
+
+
 _SIGNATURES = {
     "magi_b200_abi_version": (C.c_int, []),
     "magi_b200_model_dims": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -50,6 +57,9 @@ _SIGNATURES = {
                                                                                 C.c_size_t, C.c_void_p]),
     "magi_b200_hmc_run": (C.c_int, [C.POINTER(Problem), C.POINTER(HmcConfig)] + [C.c_void_p] * 13 +
                           [C.c_size_t, C.c_void_p]),
+    "magi_b200_nuts_leaf_pre": (C.c_int, [C.POINTER(NutsSubtree)] + [C.c_void_p] * 5),
+    "magi_b200_nuts_leaf_post": (C.c_int, [C.POINTER(NutsSubtree)] + [C.c_void_p] * 9 +
+                                 [C.c_int64, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -157,10 +157,10 @@ class MagiBatch:
         z = nuts.pack_state(X, s, tau)
         e, d = eps.reshape(-1), da.reshape(-1, 4)
         ids = torch.arange(cid0, cid0 + B * R, dtype=torch.int64, device=z.device)
-        vg = nuts.problem_value_and_grad(self.prob, R)
+        eng = nuts.FusedLeafEngine(self.prob, R)
         LB = torch.as_tensor(self.sigma_sqs_LB, dtype=torch.float64, device=z.device)[:, None]
-        burn = nuts.nuts_run_(z, e, d, vg, n_iter=num_burnin_steps, num_adapt=num_adapt, seed=seed, chain_ids=ids,
-                              max_tree_depth=max_tree_depth)
+        burn = nuts.nuts_run_(z, e, d, None, n_iter=num_burnin_steps, num_adapt=num_adapt, seed=seed, chain_ids=ids,
+                              max_tree_depth=max_tree_depth, leaf_engine=eng)
         th = torch.empty((num_results, B, R, P), dtype=torch.float64, device=z.device)
         sg = torch.empty((num_results, B, R, D), dtype=torch.float64, device=z.device)
         Xsum = torch.zeros((B, R, n * D), dtype=torch.float64, device=z.device)
@@ -173,8 +173,8 @@ class MagiBatch:
             if keep_X_mean:
                 Xsum.add_(zz[..., :n * D]); Xsq.addcmul_(zz[..., :n * D], zz[..., :n * D])
 
-        out = nuts.nuts_run_(z, e, d, vg, n_iter=num_results, iter0=num_burnin_steps, num_adapt=num_adapt, seed=seed,
-                             chain_ids=ids, max_tree_depth=max_tree_depth, on_sample=on_sample)
+        out = nuts.nuts_run_(z, e, d, None, n_iter=num_results, iter0=num_burnin_steps, num_adapt=num_adapt, seed=seed,
+                             chain_ids=ids, max_tree_depth=max_tree_depth, on_sample=on_sample, leaf_engine=eng)
         if gather and self.world > 1:
             sizes = parallel.shard_sizes(self.B_total, self.world)
             th = parallel.gather_samples(th, dataset_dim=1, sizes=sizes)

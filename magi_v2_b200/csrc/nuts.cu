@@ -1,0 +1,197 @@
+// Fused per-leaf bookkeeping of the batched No-U-Turn sampler (include/magi_b200_nuts.h).
+// Pure streaming kernels: every [C,S] array is touched once per leaf, the per-chain scalars (energy, weights,
+// U-turn dot products) are block reductions inside the same pass.  HBM-bound: ~5 array passes in `pre`, ~9-11 in
+// `post` (4 reads + 4 writes + 2 per checkpoint touched) of C*S*8 bytes each.
+#include "common.cuh"
+#include "../../include/magi_b200_nuts.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct Parts {
+  const double* X;
+  const double* s;
+  const double* t;
+};
+
+__device__ __forceinline__ double part_load(const Parts& p, int c, int i, int nD, int D, int P) {
+  if (i < nD) return p.X[(size_t)c * nD + i];
+  if (i < nD + D) return p.s[(size_t)c * D + (i - nD)];
+  return p.t[(size_t)c * P + (i - nD - D)];
+}
+
+__global__ void __launch_bounds__(kThreads) nuts_leaf_pre_kernel(magi_nuts_subtree_t st, double* __restrict__ ph,
+                                                                 double* __restrict__ Xn, double* __restrict__ sn,
+                                                                 double* __restrict__ tn) {
+  const int c = blockIdx.x;
+  const int nD = st.nD, D = st.D, P = st.P, S = nD + D + P;
+  const bool on = st.building[c] != 0;
+  const double e = st.e[c];
+  const double* zc = st.zc + (size_t)c * S;
+  const double* pc = st.pc + (size_t)c * S;
+  const double* gc = st.gc + (size_t)c * S;
+  double* phc = ph + (size_t)c * S;
+  for (int i = threadIdx.x; i < S; i += kThreads) {
+    double z = zc[i];
+    if (on) {
+      const double h = fma(0.5 * e, gc[i], pc[i]);
+      phc[i] = h;
+      z = fma(e, h, z);
+    }
+    if (i < nD) Xn[(size_t)c * nD + i] = z;
+    else if (i < nD + D) sn[(size_t)c * D + (i - nD)] = z;
+    else tn[(size_t)c * P + (i - nD - D)] = z;
+  }
+}
+
+struct Checks {
+  int n;
+  int slot[MAGI_NUTS_MAX_CHECKS];
+};
+
+__device__ __forceinline__ double logaddexp_d(double a, double b) {
+  const double m = fmax(a, b);
+  if (!(m > -INFINITY)) return m;  // both -inf (or NaN)
+  return m + log1p(exp(-fabs(a - b)));
+}
+
+__global__ void __launch_bounds__(kThreads) nuts_leaf_post_kernel(magi_nuts_subtree_t st,
+                                                                  const double* __restrict__ ph, Parts zn, Parts gn,
+                                                                  const double* __restrict__ lp_new,
+                                                                  const double* __restrict__ log_u, int64_t log_u_stride,
+                                                                  double max_energy_diff, int slot_store, Checks ck) {
+  const int c = blockIdx.x;
+  if (st.building[c] == 0) return;
+  const int nD = st.nD, D = st.D, P = st.P, S = nD + D + P, C = st.C;
+  const double he = 0.5 * st.e[c];
+  const size_t row = (size_t)c * S;
+  double* zc = st.zc + row;
+  double* pc = st.pc + row;
+  double* gc = st.gc + row;
+  double* rho = st.rho_sub + row;
+  const double* phc = ph + row;
+  double* store_p = slot_store >= 0 ? st.ck_p + ((size_t)slot_store * C + c) * S : nullptr;
+  double* store_r = slot_store >= 0 ? st.ck_rho + ((size_t)slot_store * C + c) * S : nullptr;
+
+  // acc[0] = p.p ; acc[1 + 2k] = rb_k . ck_p_k ; acc[2 + 2k] = rb_k . p
+  double acc[1 + 2 * MAGI_NUTS_MAX_CHECKS];
+#pragma unroll
+  for (int q = 0; q < 1 + 2 * MAGI_NUTS_MAX_CHECKS; ++q) acc[q] = 0.0;
+
+  for (int i = threadIdx.x; i < S; i += kThreads) {
+    const double g = part_load(gn, c, i, nD, D, P);
+    const double z = part_load(zn, c, i, nD, D, P);
+    const double p = fma(he, g, phc[i]);
+    const double r_old = rho[i];
+    const double r_new = r_old + p;
+    zc[i] = z;
+    pc[i] = p;
+    gc[i] = g;
+    rho[i] = r_new;
+    if (store_p) {
+      store_r[i] = r_old;
+      store_p[i] = p;
+    }
+    acc[0] = fma(p, p, acc[0]);
+#pragma unroll
+    for (int k = 0; k < MAGI_NUTS_MAX_CHECKS; ++k) {
+      if (k < ck.n) {
+        const size_t o = ((size_t)ck.slot[k] * C + c) * S + i;
+        const double rb = r_new - st.ck_rho[o];
+        acc[1 + 2 * k] = fma(rb, st.ck_p[o], acc[1 + 2 * k]);
+        acc[2 + 2 * k] = fma(rb, p, acc[2 + 2 * k]);
+      }
+    }
+  }
+
+  __shared__ double red[kThreads / 32][1 + 2 * MAGI_NUTS_MAX_CHECKS];
+  __shared__ int s_take;
+  const int nred = 1 + 2 * ck.n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 1 + 2 * MAGI_NUTS_MAX_CHECKS; ++q) {
+    if (q < nred) {
+      const double v = magi_warp_sum(acc[q]);
+      if (lane == 0) red[warp][q] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot[1 + 2 * MAGI_NUTS_MAX_CHECKS];
+    for (int q = 0; q < nred; ++q) {
+      double v = 0.0;
+      for (int w = 0; w < kThreads / 32; ++w) v += red[w][q];
+      tot[q] = v;
+    }
+    const double lp = lp_new[c];
+    double dE = -lp + 0.5 * tot[0] - st.H0[c];
+    if (!isfinite(dE)) dE = INFINITY;
+    st.sum_acc[c] += exp(fmin(-dE, 0.0));
+    st.n_leaf[c] += 1;
+    const bool div = dE > max_energy_diff;
+    if (div) st.diverged[c] = 1;
+    const double lw_new = logaddexp_d(st.logw_sub[c], -dE);
+    const bool take = log_u[(size_t)c * log_u_stride] < (-dE - lw_new);   // false for NaN (-inf - -inf)
+    st.logw_sub[c] = lw_new;
+    if (take) st.sub_lp[c] = lp;
+    bool ok = !div;
+    for (int k = 0; k < ck.n; ++k) ok = ok && (tot[1 + 2 * k] > 0.0) && (tot[2 + 2 * k] > 0.0);
+    st.building[c] = ok ? 1 : 0;
+    s_take = take ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_take) {
+    double* sz = st.sub_z + row;
+    for (int i = threadIdx.x; i < S; i += kThreads) sz[i] = zc[i];
+  }
+}
+
+int check_subtree(const magi_nuts_subtree_t* st) {
+  if (!st) return -1;
+  if (st->C <= 0 || st->nD <= 0 || st->D <= 0 || st->P < 0) return -1;
+  if (!st->zc || !st->pc || !st->gc || !st->rho_sub || !st->sub_z || !st->sub_lp || !st->logw_sub || !st->sum_acc ||
+      !st->n_leaf || !st->building || !st->diverged || !st->e || !st->H0)
+    return -1;
+  return MAGI_OK;
+}
+
+}  // namespace
+
+extern "C" int magi_b200_nuts_leaf_pre(const magi_nuts_subtree_t* st, double* ph, double* Xn, double* sn, double* tn,
+                                       magi_stream_t stream) {
+  if (int s = check_subtree(st)) return s;
+  if (!ph) return -2;
+  if (!Xn) return -3;
+  if (!sn) return -4;
+  if (!tn && st->P > 0) return -5;
+  nuts_leaf_pre_kernel<<<st->C, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(*st, ph, Xn, sn, tn);
+  return magi_cuda_status(cudaGetLastError());
+}
+
+extern "C" int magi_b200_nuts_leaf_post(const magi_nuts_subtree_t* st, const double* ph, const double* Xn,
+                                        const double* sn, const double* tn, const double* lp_new, const double* gX,
+                                        const double* gs, const double* gt, const double* log_u, int64_t log_u_stride,
+                                        double max_energy_diff, int slot_store, int n_checks, const int* check_slots,
+                                        magi_stream_t stream) {
+  if (int s = check_subtree(st)) return s;
+  if (!ph) return -2;
+  if (!Xn) return -3;
+  if (!sn) return -4;
+  if (!tn && st->P > 0) return -5;
+  if (!lp_new) return -6;
+  if (!gX) return -7;
+  if (!gs) return -8;
+  if (!gt && st->P > 0) return -9;
+  if (!log_u) return -10;
+  if (n_checks < 0 || n_checks > MAGI_NUTS_MAX_CHECKS) return -14;
+  if ((slot_store >= 0 || n_checks > 0) && (!st->ck_p || !st->ck_rho)) return -1;
+  if (n_checks > 0 && !check_slots) return -15;
+  Checks ck;
+  ck.n = n_checks;
+  for (int k = 0; k < MAGI_NUTS_MAX_CHECKS; ++k) ck.slot[k] = k < n_checks ? check_slots[k] : 0;
+  const Parts zn{Xn, sn, tn}, gn{gX, gs, gt};
+  nuts_leaf_post_kernel<<<st->C, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      *st, ph, zn, gn, lp_new, log_u, log_u_stride, max_energy_diff, slot_store, ck);
+  return magi_cuda_status(cudaGetLastError());
+}

@@ -245,15 +245,15 @@ class MAGI_v2:
         R, n, D, P = X.shape[1], self.mag_I, self.D, self.D_thetas
         z = nuts.pack_state(X, s, tau)
         e, d = eps.reshape(-1).clone(), da.reshape(-1, 4).clone()
-        vg = nuts.problem_value_and_grad(prob, R)
+        eng = nuts.FusedLeafEngine(prob, R)
         if verbose:
             print("Starting NUTS posterior sampling ...")
         start = time.time()
-        burn = nuts.nuts_run_(z, e, d, vg, n_iter=num_burnin_steps, iter0=0, num_adapt=num_adapt, seed=seed,
-                              max_tree_depth=max_tree_depth)
+        burn = nuts.nuts_run_(z, e, d, None, n_iter=num_burnin_steps, iter0=0, num_adapt=num_adapt, seed=seed,
+                              max_tree_depth=max_tree_depth, leaf_engine=eng)
         keep = torch.empty((num_results,) + tuple(z.shape), dtype=torch.float64, device=z.device)
-        out = nuts.nuts_run_(z, e, d, vg, n_iter=num_results, iter0=num_burnin_steps, num_adapt=num_adapt, seed=seed,
-                             max_tree_depth=max_tree_depth, on_sample=lambda it, zz, info: keep[it].copy_(zz))
+        out = nuts.nuts_run_(z, e, d, None, n_iter=num_results, iter0=num_burnin_steps, num_adapt=num_adapt, seed=seed,
+                             max_tree_depth=max_tree_depth, leaf_engine=eng, on_sample=lambda it, zz, info: keep[it].copy_(zz))
         torch.cuda.synchronize(z.device)
         minutes = np.round((time.time() - start) / 60, 2)
         if verbose:

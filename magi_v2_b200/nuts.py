@@ -101,9 +101,61 @@ def _sel(mask: Tensor, new: Tensor, old: Tensor) -> Tensor:
     return old.copy_(torch.where(m, new, old))
 
 
+def _build_subtree(sub: dict, value_and_grad) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """2^j leaves continuing from (zc, pc, gc) (updated in place) with tensor ops only: the device-agnostic form of
+    the loop body (the CUDA form is `FusedLeafEngine.build_subtree`).  Returns (rho_sub, logw_sub, sub_z, sub_lp,
+    building): momentum sum, log weight and multinomial proposal of the subtree, and which chains completed it."""
+    zc, pc, gc, e, H0, lp0 = sub["zc"], sub["pc"], sub["gc"], sub["e"], sub["H0"], sub["lp0"]
+    building, log_u_leaf, n_sub = sub["building"], sub["log_u_leaf"], sub["n_sub"]
+    sum_acc, n_leaf, diverged, ck_p, ck_rho = sub["sum_acc"], sub["n_leaf"], sub["diverged"], sub["ck_p"], sub["ck_rho"]
+    max_energy_diff, sync_every = sub["max_energy_diff"], sub["sync_every"]
+    rho_sub = torch.zeros_like(zc)
+    logw_sub = torch.full_like(H0, -math.inf)
+    sub_z, sub_lp = zc.clone(), lp0.clone()
+    for i in range(n_sub):
+        if i % sync_every == 0 and i > 0 and not bool(building.any()):
+            break
+        even = i % 2 == 0 and n_sub > 1
+        if even:
+            # an even leaf opens dyadic blocks: remember the momentum sum before it ...
+            slot = bin(i).count("1")
+            ck_rho[slot].copy_(rho_sub)
+        # one leapfrog step (TFP SimpleLeapfrogIntegrator, identity mass) with the signed step size
+        ph = pc + (0.5 * e)[:, None] * gc
+        zn = zc + e[:, None] * ph
+        lpn, gn = value_and_grad(zn)
+        pn = ph + (0.5 * e)[:, None] * gn
+        if even:
+            ck_p[slot].copy_(pn)                             # ... and its own momentum (the block's first)
+        dE = -lpn + 0.5 * _dot(pn, pn) - H0
+        dE = torch.where(torch.isfinite(dE), dE, torch.full_like(dE, math.inf))
+        sum_acc += torch.where(building, torch.exp(torch.clamp(-dE, max=0.0)), torch.zeros_like(dE))
+        n_leaf += building.to(torch.int64)
+        div = dE > max_energy_diff
+        diverged |= building & div
+        lw_new = torch.logaddexp(logw_sub, -dE)
+        take = building & (log_u_leaf[:, i] < (-dE - lw_new))
+        _sel(take, zn, sub_z)
+        _sel(take, lpn, sub_lp)
+        _sel(building, lw_new, logw_sub)
+        rho_sub = rho_sub + torch.where(building[:, None], pn, torch.zeros_like(pn))
+        _sel(building, zn, zc); _sel(building, pn, pc); _sel(building, gn, gc)
+        ok = ~div
+        if i % 2 == 1:
+            # dyadic blocks [i - 2^k + 1, i] that end here, k = 1 .. number of trailing ones of i
+            t = (~i & (i + 1)).bit_length() - 1
+            for k in range(1, t + 1):
+                s = i - (1 << k) + 1
+                slot = bin(s).count("1")
+                rb = rho_sub - ck_rho[slot]
+                ok = ok & (_dot(rb, ck_p[slot]) > 0.0) & (_dot(rb, pn) > 0.0)
+        building = building & ok
+    return rho_sub, logw_sub, sub_z, sub_lp, building
+
+
 def nuts_transition(z: Tensor, eps: Tensor, value_and_grad: Callable[[Tensor], Tuple[Tensor, Tensor]], seed: int,
                     chain_ids: Tensor, iteration: int, max_tree_depth: int = 10, max_energy_diff: float = 1000.0,
-                    sync_every: int = 8) -> Dict[str, Tensor]:
+                    sync_every: int = 8, leaf_engine=None) -> Dict[str, Tensor]:
     """z [C, S] (updated in place to the selected proposals), eps [C] step sizes, value_and_grad(z) -> (lp [C], g [C, S]).
     Returns accept_stat [C], n_leapfrog [C] (leaves evaluated while the chain was still building), depth [C],
     diverged [C], lp [C] (log-posterior of the new state)."""
@@ -125,10 +177,10 @@ def nuts_transition(z: Tensor, eps: Tensor, value_and_grad: Callable[[Tensor], T
     depth_out = torch.zeros(C, dtype=torch.int64, device=dev)
     diverged = torch.zeros(C, dtype=torch.bool, device=dev)
     active = torch.ones(C, dtype=torch.bool, device=dev)       # still doubling
-    ninf = torch.full((C,), -math.inf, dtype=f64, device=dev)
     # checkpoint memory: slot popcount(i) holds, for the even leaf i, its momentum and the momentum sum before it
-    ck_p = [torch.empty_like(z) for _ in range(max(max_tree_depth - 1, 1))]
-    ck_rho = [torch.empty_like(z) for _ in range(max(max_tree_depth - 1, 1))]
+    n_slots = max(max_tree_depth - 1, 1)
+    ck_p = torch.empty((n_slots,) + tuple(z.shape), dtype=f64, device=dev)
+    ck_rho = torch.empty((n_slots,) + tuple(z.shape), dtype=f64, device=dev)
 
     for j in range(max_tree_depth):
         if not bool(active.any()):
@@ -139,51 +191,15 @@ def nuts_transition(z: Tensor, eps: Tensor, value_and_grad: Callable[[Tensor], T
         # the subtree starts from the end the direction points to
         fm = fwd[:, None]
         zc, pc, gc = torch.where(fm, zr, zl), torch.where(fm, pr, pl), torch.where(fm, gr, gl)
-        rho_sub = torch.zeros_like(z)
-        logw_sub = ninf.clone()
-        sub_z, sub_lp = zc.clone(), lp0.clone()
-        building = active.clone()                               # this subtree is still being built and is valid
         n_sub = 1 << j
         u_leaf, _ = rng_uniform_pairs(seed, chain_ids, iteration, RNG_NUTS_LEAF, n_sub - 1, n_sub)
-        log_u_leaf = torch.log(u_leaf)
-        for i in range(n_sub):
-            if i % sync_every == 0 and i > 0 and not bool(building.any()):
-                break
-            even = i % 2 == 0 and n_sub > 1
-            if even:
-                # an even leaf opens dyadic blocks: remember the momentum sum before it ...
-                slot = bin(i).count("1")
-                ck_rho[slot].copy_(rho_sub)
-            # one leapfrog step (TFP SimpleLeapfrogIntegrator, identity mass) with the signed step size
-            ph = pc + (0.5 * e)[:, None] * gc
-            zn = zc + e[:, None] * ph
-            lpn, gn = value_and_grad(zn)
-            pn = ph + (0.5 * e)[:, None] * gn
-            if even:
-                ck_p[slot].copy_(pn)                             # ... and its own momentum (the block's first)
-            dE = -lpn + 0.5 * _dot(pn, pn) - H0
-            dE = torch.where(torch.isfinite(dE), dE, torch.full_like(dE, math.inf))
-            sum_acc += torch.where(building, torch.exp(torch.clamp(-dE, max=0.0)), torch.zeros_like(dE))
-            n_leaf += building.to(torch.int64)
-            div = dE > max_energy_diff
-            diverged |= building & div
-            lw_new = torch.logaddexp(logw_sub, -dE)
-            take = building & (log_u_leaf[:, i] < (-dE - lw_new))
-            _sel(take, zn, sub_z)
-            _sel(take, lpn, sub_lp)
-            _sel(building, lw_new, logw_sub)
-            rho_sub = rho_sub + torch.where(building[:, None], pn, torch.zeros_like(pn))
-            _sel(building, zn, zc); _sel(building, pn, pc); _sel(building, gn, gc)
-            ok = ~div
-            if i % 2 == 1:
-                # dyadic blocks [i - 2^k + 1, i] that end here, k = 1 .. number of trailing ones of i
-                t = (~i & (i + 1)).bit_length() - 1
-                for k in range(1, t + 1):
-                    s = i - (1 << k) + 1
-                    slot = bin(s).count("1")
-                    rb = rho_sub - ck_rho[slot]
-                    ok = ok & (_dot(rb, ck_p[slot]) > 0.0) & (_dot(rb, pn) > 0.0)
-            building = building & ok
+        sub = dict(zc=zc, pc=pc, gc=gc, e=e, H0=H0, lp0=lp0, building=active.clone(), log_u_leaf=torch.log(u_leaf),
+                   sum_acc=sum_acc, n_leaf=n_leaf, diverged=diverged, ck_p=ck_p, ck_rho=ck_rho, n_sub=n_sub,
+                   max_energy_diff=max_energy_diff, sync_every=sync_every)
+        if leaf_engine is None:
+            rho_sub, logw_sub, sub_z, sub_lp, building = _build_subtree(sub, value_and_grad)
+        else:
+            rho_sub, logw_sub, sub_z, sub_lp, building = leaf_engine.build_subtree(sub)
         # merge the completed subtrees
         done = building
         swap = done & (torch.log(u_acc[:, j]) < (logw_sub - logw))
@@ -223,14 +239,18 @@ def dual_averaging_update_(eps: Tensor, da: Tensor, accept: Tensor, num_adapt: i
     da[:, 3] = step + 1.0
 
 
-def nuts_run_(z: Tensor, eps: Tensor, da: Tensor, value_and_grad_at: Callable[[Tensor, float], Tuple[Tensor, Tensor]],
+def nuts_run_(z: Tensor, eps: Tensor, da: Tensor,
+              value_and_grad_at: Optional[Callable[[Tensor, float], Tuple[Tensor, Tensor]]],
               *, n_iter: int, iter0: int = 0, num_adapt: int = 0, min_temp: float = 0.1,
               fixed_beta_temp: Optional[float] = None, target_accept: float = 0.75, seed: int = 0,
               chain_ids: Optional[Tensor] = None, max_tree_depth: int = 10,
-              on_sample: Optional[Callable[[int, Tensor, Dict[str, Tensor]], None]] = None) -> Dict[str, Tensor]:
+              on_sample: Optional[Callable[[int, Tensor, Dict[str, Tensor]], None]] = None,
+              leaf_engine: Optional["FusedLeafEngine"] = None) -> Dict[str, Tensor]:
     """n_iter NUTS transitions in place on z [C, S], eps [C], da [C, 4].  value_and_grad_at(z, beta_temp) evaluates
     the tempered log-posterior (magi_v2.py:348) at temperature beta_temp = max(1 / log(step + 2), min_temp)
-    (:833-835, :855) of the global iteration.  `on_sample(it, z, info)` is called after every transition."""
+    (:833-835, :855) of the global iteration.  `on_sample(it, z, info)` is called after every transition.  With a
+    `leaf_engine` (the product path: `FusedLeafEngine`) the evaluations and the per-leaf bookkeeping are the CUDA
+    kernels and `value_and_grad_at` is not used."""
     C = z.shape[0]
     if chain_ids is None:
         chain_ids = torch.arange(C, dtype=torch.int64, device=z.device)
@@ -241,7 +261,12 @@ def nuts_run_(z: Tensor, eps: Tensor, da: Tensor, value_and_grad_at: Callable[[T
     for it in range(n_iter):
         g_it = iter0 + it
         bt = float(fixed_beta_temp) if fixed_beta_temp else max(1.0 / math.log(g_it + 2.0), min_temp)
-        info = nuts_transition(z, eps, lambda zz: value_and_grad_at(zz, bt), seed, chain_ids, g_it, max_tree_depth)
+        if leaf_engine is not None:
+            leaf_engine.set_beta_temp(bt)
+            info = nuts_transition(z, eps, leaf_engine.value_and_grad, seed, chain_ids, g_it, max_tree_depth,
+                                   leaf_engine=leaf_engine)
+        else:
+            info = nuts_transition(z, eps, lambda zz: value_and_grad_at(zz, bt), seed, chain_ids, g_it, max_tree_depth)
         dual_averaging_update_(eps, da, info["accept_stat"], num_adapt, target_accept)
         acc[it], nleap[it], lps[it], div[it] = info["accept_stat"], info["n_leapfrog"], info["lp"], info["diverged"]
         if on_sample is not None:
@@ -273,3 +298,74 @@ def pack_state(X: Tensor, s: Tensor, tau: Tensor) -> Tensor:
     """[B,R,n,D], [B,R,D], [B,R,P] -> z [B*R, n*D + D + P]."""
     B, R = X.shape[:2]
     return torch.cat([X.reshape(B * R, -1), s.reshape(B * R, -1), tau.reshape(B * R, -1)], dim=1).contiguous()
+
+
+class FusedLeafEngine:
+    """The loop body of the tree builder as three launches per leaf (include/magi_b200_nuts.h):
+    `magi_b200_nuts_leaf_pre` -> `magi_b200_logpost_grad` -> `magi_b200_nuts_leaf_post`.  Every [C, S] array is read or
+    written once per leaf and chains whose subtree has ended are skipped by the bookkeeping kernels."""
+
+    def __init__(self, prob, R: int):
+        from . import _lib
+        self._lib, self.prob, self.R = _lib, prob, R
+        self.C, self.nD, self.D, self.P = prob.B * R, prob.n * prob.D, prob.D, prob.P
+        self.S = self.nD + self.D + self.P
+        dev, f64 = prob.device, torch.float64
+        B, n, D, P = prob.B, prob.n, prob.D, prob.P
+        self.ph = torch.empty((self.C, self.S), dtype=f64, device=dev)
+        self.Xn = torch.empty((B, R, n, D), dtype=f64, device=dev)
+        self.sn = torch.empty((B, R, D), dtype=f64, device=dev)
+        self.tn = torch.empty((B, R, P), dtype=f64, device=dev)
+        self.out = prob.logpost_grad_out(R)
+        self.bt = torch.empty((B, R), dtype=f64, device=dev)
+        self.beta_temp = None
+
+    def set_beta_temp(self, beta_temp: float):
+        if beta_temp != self.beta_temp:
+            self.bt.fill_(float(beta_temp))
+            self.beta_temp = beta_temp
+
+    def value_and_grad(self, z: Tensor):
+        """Generic evaluation at a packed state (once per transition, for the starting point)."""
+        B, R, n, D, P, nD = self.prob.B, self.R, self.prob.n, self.D, self.P, self.nD
+        lp, gX, gs, gt = self.prob.logpost_grad(z[:, :nD].reshape(B, R, n, D).contiguous(),
+                                                z[:, nD:nD + D].reshape(B, R, D).contiguous(),
+                                                z[:, nD + D:].reshape(B, R, P).contiguous(), self.bt)
+        return lp.reshape(self.C), torch.cat([gX.reshape(self.C, nD), gs.reshape(self.C, D), gt.reshape(self.C, P)], 1)
+
+    def build_subtree(self, sub: dict):
+        import ctypes as Ct
+        L, lib = self._lib, self._lib.lib()
+        zc, pc, gc, e, H0, lp0 = sub["zc"], sub["pc"], sub["gc"], sub["e"], sub["H0"], sub["lp0"]
+        building, log_u_leaf, n_sub = sub["building"], sub["log_u_leaf"], sub["n_sub"]
+        for t in (zc, pc, gc, e, H0, log_u_leaf, sub["ck_p"], sub["ck_rho"], sub["sum_acc"], sub["n_leaf"]):
+            if not (t.is_cuda and t.is_contiguous()):
+                raise RuntimeError("magi_b200: the fused NUTS path needs contiguous CUDA tensors (no CPU fallback)")
+        rho_sub = torch.zeros_like(zc)
+        logw_sub = torch.full_like(H0, -math.inf)
+        sub_z, sub_lp = zc.clone(), lp0.clone()
+        ptr = lambda t: Ct.c_void_p(t.data_ptr())
+        st = L.NutsSubtree(self.C, self.nD, self.D, self.P, ptr(zc), ptr(pc), ptr(gc), ptr(rho_sub), ptr(sub_z),
+                           ptr(sub_lp), ptr(logw_sub), ptr(sub["sum_acc"]), ptr(sub["n_leaf"]), ptr(building),
+                           ptr(sub["diverged"]), ptr(sub["ck_p"]), ptr(sub["ck_rho"]), ptr(e), ptr(H0))
+        lp, gX, gs, gt = self.out
+        with torch.cuda.device(zc.device):
+            stream = Ct.c_void_p(torch.cuda.current_stream(zc.device).cuda_stream)
+            for i in range(n_sub):
+                if i % sub["sync_every"] == 0 and i > 0 and not bool(building.any()):
+                    break
+                L.check(lib.magi_b200_nuts_leaf_pre(Ct.byref(st), ptr(self.ph), ptr(self.Xn), ptr(self.sn),
+                                                    ptr(self.tn), stream), "nuts_leaf_pre")
+                self.prob.logpost_grad(self.Xn, self.sn, self.tn, self.bt, out=self.out)
+                slot_store = bin(i).count("1") if (i % 2 == 0 and n_sub > 1) else -1
+                slots = []
+                if i % 2 == 1:
+                    t = (~i & (i + 1)).bit_length() - 1
+                    slots = [bin(i - (1 << k) + 1).count("1") for k in range(1, t + 1)]
+                arr = (Ct.c_int * max(len(slots), 1))(*slots)
+                L.check(lib.magi_b200_nuts_leaf_post(Ct.byref(st), ptr(self.ph), ptr(self.Xn), ptr(self.sn),
+                                                     ptr(self.tn), ptr(lp), ptr(gX), ptr(gs), ptr(gt),
+                                                     Ct.c_void_p(log_u_leaf.data_ptr() + 8 * i), n_sub,
+                                                     float(sub["max_energy_diff"]), slot_store, len(slots), arr,
+                                                     stream), "nuts_leaf_post")
+        return rho_sub, logw_sub, sub_z, sub_lp, building

@@ -1,4 +1,4 @@
-"""The C-ABI library loads and exports every symbol include/magi_b200.h declares (no compute calls:
+"""The C-ABI library loads and exports every symbol include/*.h declares (no compute calls:
 there is no GPU in the CPU test tier), and the product has no route into oracle/."""
 import ctypes
 import os
@@ -13,7 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
-    src = open(os.path.join(ROOT, "include", "magi_b200.h")).read()
+    inc = os.path.join(ROOT, "include")
+    src = "".join(open(os.path.join(inc, f)).read() for f in sorted(os.listdir(inc)) if f.endswith(".h"))
     return sorted(set(re.findall(r"MAGI_API\s+[\w\s\*]+?\b(magi_b200_\w+)\s*\(", src)))
 
 

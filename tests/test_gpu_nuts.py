@@ -18,8 +18,8 @@ def _T(a, device):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=device)
 
 
-@pytest.mark.parametrize("model", ["seir3", "sirw"])
-def test_nuts_chain_matches_oracle_draw_for_draw(model, cuda_device):
+@pytest.mark.parametrize("model,fused", [("seir3", True), ("sirw", True), ("seir3", False), ("lorenz96", True)])
+def test_nuts_chain_matches_oracle_draw_for_draw(model, fused, cuda_device):
     import torch
     from magi_v2_b200 import nuts
     rng = np.random.default_rng(7)
@@ -35,8 +35,10 @@ def test_nuts_chain_matches_oracle_draw_for_draw(model, cuda_device):
     da = torch.zeros((B * R, 4), dtype=torch.float64, device=cuda_device)
     da[:, 2] = float(np.log(10.0 * eps0))
     keep = []
+    # fused: the product path (CUDA bookkeeping kernels); not fused: the tensor-op form of the same loop body
     out = nuts.nuts_run_(z, eps, da, nuts.problem_value_and_grad(prob, R), n_iter=n_iter, num_adapt=num_adapt,
-                         seed=seed, max_tree_depth=max_depth, on_sample=lambda it, zz, info: keep.append(zz.cpu().numpy()))
+                         seed=seed, max_tree_depth=max_depth, on_sample=lambda it, zz, info: keep.append(zz.cpu().numpy()),
+                         leaf_engine=nuts.FusedLeafEngine(prob, R) if fused else None)
     torch.cuda.synchronize()
     nl = out["n_leapfrog"].cpu().numpy()
     acc = out["accept_prob"].cpu().numpy()
