@@ -68,6 +68,39 @@ MAGI_API int magi_b200_nuts_leaf_post(const magi_nuts_subtree_t* st, const doubl
                                       double max_energy_diff, int slot_store, int n_checks,
                                       const int* check_slots /* host, n_checks entries */, magi_stream_t stream);
 
+/* The tree of the current transition, [C,S] / [C] device arrays. */
+typedef struct {
+  double* zl;             /* [C,S] leftmost state: position, momentum, gradient */
+  double* pl;
+  double* gl;
+  double* zr;             /* [C,S] rightmost state */
+  double* pr;
+  double* gr;
+  double* rho;            /* [C,S] sum of the momenta of every leaf of the tree */
+  double* prop_z;         /* [C,S] the transition's current proposal ... */
+  double* prop_lp;        /* [C]   ... and its log-posterior */
+  double* logw;           /* [C]   log of the tree's total weight */
+  uint8_t* active;        /* [C]   out of `merge`: 1 = the chain goes on doubling */
+  const uint8_t* fwd;     /* [C]   direction of the current doubling: 1 = forward (extends the right end) */
+} magi_nuts_tree_t;
+
+/* Momentum draw of a transition: p0 [C,S] standard normals from the sampler's counter-based stream
+ * (Philox4x32-10, counter = (pair index, chain_ids[c], iteration, 0), key = seed; Box-Muller) -- the same numbers
+ * `magi_b200_hmc_run` draws for that chain and iteration.  chain_ids: [C] int64 device array. */
+MAGI_API int magi_b200_nuts_momentum(uint64_t seed, const int64_t* chain_ids, uint32_t iteration, int C, int S,
+                                     double* p0, magi_stream_t stream);
+
+/* Start of a doubling: (zc, pc, gc) <- the end of the tree the direction points to, rho_sub <- 0, sub_z <- zc. */
+MAGI_API int magi_b200_nuts_subtree_begin(const magi_nuts_subtree_t* st, const magi_nuts_tree_t* tree,
+                                          magi_stream_t stream);
+
+/* End of a doubling, for the chains whose subtree completed (building = 1; the others get active = 0 and keep their
+ * tree): biased progressive sampling (the subtree's proposal replaces the tree's when log_u_acc < logw_sub - logw),
+ * logw <- logaddexp(logw, logw_sub), rho += rho_sub, the extended end <- (zc, pc, gc), and the generalised U-turn
+ * criterion of the whole tree: active <- rho.p_left > 0 && rho.p_right > 0.  log_u_acc [C]. */
+MAGI_API int magi_b200_nuts_merge(const magi_nuts_subtree_t* st, const magi_nuts_tree_t* tree, const double* log_u_acc,
+                                  magi_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -38,6 +38,12 @@ class NutsSubtree(C.Structure):
                                           "building", "diverged", "ck_p", "ck_rho", "e", "H0")]
 
 
+class NutsTree(C.Structure):
+    """magi_nuts_tree_t (include/magi_b200_nuts.h)"""
+    _fields_ = [(k, C.c_void_p) for k in ("zl", "pl", "gl", "zr", "pr", "gr", "rho", "prop_z", "prop_lp", "logw",
+                                          "active", "fwd")]
+
+
 _SIGNATURES = {
     "magi_b200_abi_version": (C.c_int, []),
     "magi_b200_model_dims": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -57,6 +63,9 @@ _SIGNATURES = {
                                                                                 C.c_size_t, C.c_void_p]),
     "magi_b200_hmc_run": (C.c_int, [C.POINTER(Problem), C.POINTER(HmcConfig)] + [C.c_void_p] * 13 +
                           [C.c_size_t, C.c_void_p]),
+    "magi_b200_nuts_momentum": (C.c_int, [C.c_uint64, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "magi_b200_nuts_subtree_begin": (C.c_int, [C.POINTER(NutsSubtree), C.POINTER(NutsTree), C.c_void_p]),
+    "magi_b200_nuts_merge": (C.c_int, [C.POINTER(NutsSubtree), C.POINTER(NutsTree), C.c_void_p, C.c_void_p]),
     "magi_b200_nuts_leaf_pre": (C.c_int, [C.POINTER(NutsSubtree)] + [C.c_void_p] * 5),
     "magi_b200_nuts_leaf_post": (C.c_int, [C.POINTER(NutsSubtree)] + [C.c_void_p] * 9 +
                                  [C.c_int64, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]),

@@ -3,6 +3,7 @@
 // U-turn dot products) are block reductions inside the same pass.  HBM-bound: ~5 array passes in `pre`, ~9-11 in
 // `post` (4 reads + 4 writes + 2 per checkpoint touched) of C*S*8 bytes each.
 #include "common.cuh"
+#include "rng.cuh"
 #include "../../include/magi_b200_nuts.h"
 
 namespace {
@@ -147,6 +148,87 @@ __global__ void __launch_bounds__(kThreads) nuts_leaf_post_kernel(magi_nuts_subt
   }
 }
 
+__global__ void __launch_bounds__(kThreads) nuts_momentum_kernel(uint64_t seed, const int64_t* __restrict__ chain_ids,
+                                                                 uint32_t iteration, int S, double* __restrict__ p0) {
+  const int c = blockIdx.y;
+  const int pair = blockIdx.x * kThreads + threadIdx.x;
+  if (2 * pair >= S) return;
+  double z0, z1;
+  magi_normal_pair(seed, (uint32_t)pair, (uint32_t)chain_ids[c], iteration, z0, z1);
+  double* row = p0 + (size_t)c * S;
+  row[2 * pair] = z0;
+  if (2 * pair + 1 < S) row[2 * pair + 1] = z1;
+}
+
+__global__ void __launch_bounds__(kThreads) nuts_begin_kernel(magi_nuts_subtree_t st, magi_nuts_tree_t tr) {
+  const int c = blockIdx.x;
+  const int S = st.nD + st.D + st.P;
+  const size_t row = (size_t)c * S;
+  const bool fwd = tr.fwd[c] != 0;
+  const double* sz = (fwd ? tr.zr : tr.zl) + row;
+  const double* sp = (fwd ? tr.pr : tr.pl) + row;
+  const double* sg = (fwd ? tr.gr : tr.gl) + row;
+  for (int i = threadIdx.x; i < S; i += kThreads) {
+    const double z = sz[i];
+    st.zc[row + i] = z;
+    st.pc[row + i] = sp[i];
+    st.gc[row + i] = sg[i];
+    st.rho_sub[row + i] = 0.0;
+    st.sub_z[row + i] = z;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) nuts_merge_kernel(magi_nuts_subtree_t st, magi_nuts_tree_t tr,
+                                                              const double* __restrict__ log_u_acc) {
+  const int c = blockIdx.x;
+  if (st.building[c] == 0) {
+    if (threadIdx.x == 0) tr.active[c] = 0;
+    return;
+  }
+  const int S = st.nD + st.D + st.P;
+  const size_t row = (size_t)c * S;
+  const bool fwd = tr.fwd[c] != 0;
+  const double lw_sub = st.logw_sub[c], lw = tr.logw[c];
+  const bool swap = log_u_acc[c] < (lw_sub - lw);
+  double* dz = (fwd ? tr.zr : tr.zl) + row;
+  double* dp = (fwd ? tr.pr : tr.pl) + row;
+  double* dg = (fwd ? tr.gr : tr.gl) + row;
+  const double* op = (fwd ? tr.pl : tr.pr) + row;
+  double a0 = 0.0, a1 = 0.0;
+  for (int i = threadIdx.x; i < S; i += kThreads) {
+    const double r = tr.rho[row + i] + st.rho_sub[row + i];
+    const double p = st.pc[row + i];
+    tr.rho[row + i] = r;
+    dz[i] = st.zc[row + i];
+    dp[i] = p;
+    dg[i] = st.gc[row + i];
+    if (swap) tr.prop_z[row + i] = st.sub_z[row + i];
+    a0 = fma(r, p, a0);
+    a1 = fma(r, op[i], a1);
+  }
+  __shared__ double red[kThreads / 32][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  a0 = magi_warp_sum(a0);
+  a1 = magi_warp_sum(a1);
+  if (lane == 0) { red[warp][0] = a0; red[warp][1] = a1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) { t0 += red[w][0]; t1 += red[w][1]; }
+    tr.logw[c] = logaddexp_d(lw, lw_sub);
+    if (swap) tr.prop_lp[c] = st.sub_lp[c];
+    tr.active[c] = (t0 > 0.0 && t1 > 0.0) ? 1 : 0;
+  }
+}
+
+int check_tree(const magi_nuts_tree_t* t) {
+  if (!t) return -2;
+  if (!t->zl || !t->pl || !t->gl || !t->zr || !t->pr || !t->gr || !t->rho || !t->prop_z || !t->prop_lp || !t->logw ||
+      !t->active || !t->fwd)
+    return -2;
+  return MAGI_OK;
+}
+
 int check_subtree(const magi_nuts_subtree_t* st) {
   if (!st) return -1;
   if (st->C <= 0 || st->nD <= 0 || st->D <= 0 || st->P < 0) return -1;
@@ -193,5 +275,39 @@ extern "C" int magi_b200_nuts_leaf_post(const magi_nuts_subtree_t* st, const dou
   const Parts zn{Xn, sn, tn}, gn{gX, gs, gt};
   nuts_leaf_post_kernel<<<st->C, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       *st, ph, zn, gn, lp_new, log_u, log_u_stride, max_energy_diff, slot_store, ck);
+  return magi_cuda_status(cudaGetLastError());
+}
+
+extern "C" int magi_b200_nuts_momentum(uint64_t seed, const int64_t* chain_ids, uint32_t iteration, int C, int S,
+                                       double* p0, magi_stream_t stream) {
+  if (!chain_ids) return -2;
+  if (C <= 0 || C > 65535 * 32) return -4;
+  if (S <= 0) return -5;
+  if (!p0) return -6;
+  const int npair = (S + 1) / 2;
+  // gridDim.y <= 65535: launch in slabs of chains
+  for (int c0 = 0; c0 < C; c0 += 65535) {
+    const int nc = C - c0 < 65535 ? C - c0 : 65535;
+    const dim3 grid((npair + kThreads - 1) / kThreads, nc);
+    nuts_momentum_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(seed, chain_ids + c0, iteration, S,
+                                                                                  p0 + (size_t)c0 * S);
+  }
+  return magi_cuda_status(cudaGetLastError());
+}
+
+extern "C" int magi_b200_nuts_subtree_begin(const magi_nuts_subtree_t* st, const magi_nuts_tree_t* tree,
+                                            magi_stream_t stream) {
+  if (int s = check_subtree(st)) return s;
+  if (int s = check_tree(tree)) return s;
+  nuts_begin_kernel<<<st->C, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(*st, *tree);
+  return magi_cuda_status(cudaGetLastError());
+}
+
+extern "C" int magi_b200_nuts_merge(const magi_nuts_subtree_t* st, const magi_nuts_tree_t* tree, const double* log_u_acc,
+                                    magi_stream_t stream) {
+  if (int s = check_subtree(st)) return s;
+  if (int s = check_tree(tree)) return s;
+  if (!log_u_acc) return -3;
+  nuts_merge_kernel<<<st->C, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(*st, *tree, log_u_acc);
   return magi_cuda_status(cudaGetLastError());
 }

@@ -163,7 +163,10 @@ def nuts_transition(z: Tensor, eps: Tensor, value_and_grad: Callable[[Tensor], T
     dev, f64 = z.device, torch.float64
     lp0, g0 = value_and_grad(z)
     lp0, g0 = lp0.clone(), g0.clone()
-    p0 = rng_normals(seed, chain_ids, iteration, S)
+    if leaf_engine is None:
+        p0 = rng_normals(seed, chain_ids, iteration, S)
+    else:
+        p0 = leaf_engine.momentum(seed, chain_ids, iteration)
     H0 = -lp0 + 0.5 * _dot(p0, p0)
     u_dir, u_acc = rng_uniform_pairs(seed, chain_ids, iteration, RNG_NUTS_DEPTH, 0, max_tree_depth)
 
@@ -179,8 +182,11 @@ def nuts_transition(z: Tensor, eps: Tensor, value_and_grad: Callable[[Tensor], T
     active = torch.ones(C, dtype=torch.bool, device=dev)       # still doubling
     # checkpoint memory: slot popcount(i) holds, for the even leaf i, its momentum and the momentum sum before it
     n_slots = max(max_tree_depth - 1, 1)
-    ck_p = torch.empty((n_slots,) + tuple(z.shape), dtype=f64, device=dev)
-    ck_rho = torch.empty((n_slots,) + tuple(z.shape), dtype=f64, device=dev)
+    if leaf_engine is None:
+        ck_p = torch.empty((n_slots,) + tuple(z.shape), dtype=f64, device=dev)
+        ck_rho = torch.empty((n_slots,) + tuple(z.shape), dtype=f64, device=dev)
+    else:
+        ck_p, ck_rho = leaf_engine.checkpoints(n_slots)
 
     for j in range(max_tree_depth):
         if not bool(active.any()):
@@ -188,25 +194,32 @@ def nuts_transition(z: Tensor, eps: Tensor, value_and_grad: Callable[[Tensor], T
         depth_out += active.to(torch.int64)
         fwd = u_dir[:, j] < 0.5
         e = torch.where(fwd, eps, -eps)
-        # the subtree starts from the end the direction points to
-        fm = fwd[:, None]
-        zc, pc, gc = torch.where(fm, zr, zl), torch.where(fm, pr, pl), torch.where(fm, gr, gl)
         n_sub = 1 << j
         u_leaf, _ = rng_uniform_pairs(seed, chain_ids, iteration, RNG_NUTS_LEAF, n_sub - 1, n_sub)
-        sub = dict(zc=zc, pc=pc, gc=gc, e=e, H0=H0, lp0=lp0, building=active.clone(), log_u_leaf=torch.log(u_leaf),
+        sub = dict(e=e, H0=H0, lp0=lp0, building=active.clone(), log_u_leaf=torch.log(u_leaf),
                    sum_acc=sum_acc, n_leaf=n_leaf, diverged=diverged, ck_p=ck_p, ck_rho=ck_rho, n_sub=n_sub,
                    max_energy_diff=max_energy_diff, sync_every=sync_every)
-        if leaf_engine is None:
-            rho_sub, logw_sub, sub_z, sub_lp, building = _build_subtree(sub, value_and_grad)
-        else:
-            rho_sub, logw_sub, sub_z, sub_lp, building = leaf_engine.build_subtree(sub)
+        log_u_acc = torch.log(u_acc[:, j])
+        if leaf_engine is not None:
+            # the product path: begin / per-leaf / merge kernels of include/magi_b200_nuts.h
+            tree = dict(zl=zl, pl=pl, gl=gl, zr=zr, pr=pr, gr=gr, rho=rho, prop_z=prop_z, prop_lp=prop_lp, logw=logw,
+                        fwd=fwd)
+            leaf_engine.begin(sub, tree)
+            leaf_engine.build_subtree(sub)
+            active = leaf_engine.merge(tree, log_u_acc)
+            continue
+        # the same steps with tensor ops: the subtree starts from the end the direction points to
+        fm = fwd[:, None]
+        sub["zc"], sub["pc"], sub["gc"] = torch.where(fm, zr, zl), torch.where(fm, pr, pl), torch.where(fm, gr, gl)
+        zc, pc, gc = sub["zc"], sub["pc"], sub["gc"]
+        rho_sub, logw_sub, sub_z, sub_lp, building = _build_subtree(sub, value_and_grad)
         # merge the completed subtrees
         done = building
-        swap = done & (torch.log(u_acc[:, j]) < (logw_sub - logw))
+        swap = done & (log_u_acc < (logw_sub - logw))
         _sel(swap, sub_z, prop_z)
         _sel(swap, sub_lp, prop_lp)
         _sel(done, torch.logaddexp(logw, logw_sub), logw)
-        rho = rho + torch.where(done[:, None], rho_sub, torch.zeros_like(rho_sub))
+        rho += torch.where(done[:, None], rho_sub, torch.zeros_like(rho_sub))
         mr, ml = done & fwd, done & ~fwd
         _sel(mr, zc, zr); _sel(mr, pc, pr); _sel(mr, gc, gr)
         _sel(ml, zc, zl); _sel(ml, pc, pl); _sel(ml, gc, gl)
@@ -301,9 +314,10 @@ def pack_state(X: Tensor, s: Tensor, tau: Tensor) -> Tensor:
 
 
 class FusedLeafEngine:
-    """The loop body of the tree builder as three launches per leaf (include/magi_b200_nuts.h):
-    `magi_b200_nuts_leaf_pre` -> `magi_b200_logpost_grad` -> `magi_b200_nuts_leaf_post`.  Every [C, S] array is read or
-    written once per leaf and chains whose subtree has ended are skipped by the bookkeeping kernels."""
+    """The tree builder's steps as CUDA kernels (include/magi_b200_nuts.h): the momentum draw, per doubling
+    `magi_b200_nuts_subtree_begin` and `magi_b200_nuts_merge`, and per leaf `magi_b200_nuts_leaf_pre` ->
+    `magi_b200_logpost_grad` -> `magi_b200_nuts_leaf_post`.  Every [C, S] array is read or written once per step and
+    chains whose subtree has ended are skipped by the bookkeeping kernels.  CUDA only: no CPU fallback."""
 
     def __init__(self, prob, R: int):
         from . import _lib
@@ -312,18 +326,30 @@ class FusedLeafEngine:
         self.S = self.nD + self.D + self.P
         dev, f64 = prob.device, torch.float64
         B, n, D, P = prob.B, prob.n, prob.D, prob.P
-        self.ph = torch.empty((self.C, self.S), dtype=f64, device=dev)
-        self.Xn = torch.empty((B, R, n, D), dtype=f64, device=dev)
-        self.sn = torch.empty((B, R, D), dtype=f64, device=dev)
-        self.tn = torch.empty((B, R, P), dtype=f64, device=dev)
+        mk = lambda *sh: torch.empty(sh, dtype=f64, device=dev)
+        self.ph, self.zc, self.pc, self.gc, self.rho_sub, self.sub_z = (mk(self.C, self.S) for _ in range(6))
+        self.sub_lp, self.logw_sub = mk(self.C), mk(self.C)
+        self.Xn, self.sn, self.tn = mk(B, R, n, D), mk(B, R, D), mk(B, R, P)
         self.out = prob.logpost_grad_out(R)
-        self.bt = torch.empty((B, R), dtype=f64, device=dev)
+        self.bt = mk(B, R)
         self.beta_temp = None
+        self._ck = None
+        self._st = None
+
+    def _stream(self):
+        import ctypes as Ct
+        return Ct.c_void_p(torch.cuda.current_stream(self.prob.device).cuda_stream)
 
     def set_beta_temp(self, beta_temp: float):
         if beta_temp != self.beta_temp:
             self.bt.fill_(float(beta_temp))
             self.beta_temp = beta_temp
+
+    def checkpoints(self, n_slots: int):
+        if self._ck is None or self._ck[0].shape[0] < n_slots:
+            self._ck = tuple(torch.empty((n_slots, self.C, self.S), dtype=torch.float64, device=self.prob.device)
+                             for _ in range(2))
+        return self._ck
 
     def value_and_grad(self, z: Tensor):
         """Generic evaluation at a packed state (once per transition, for the starting point)."""
@@ -333,24 +359,54 @@ class FusedLeafEngine:
                                                 z[:, nD + D:].reshape(B, R, P).contiguous(), self.bt)
         return lp.reshape(self.C), torch.cat([gX.reshape(self.C, nD), gs.reshape(self.C, D), gt.reshape(self.C, P)], 1)
 
-    def build_subtree(self, sub: dict):
+    def momentum(self, seed: int, chain_ids: Tensor, iteration: int) -> Tensor:
         import ctypes as Ct
-        L, lib = self._lib, self._lib.lib()
-        zc, pc, gc, e, H0, lp0 = sub["zc"], sub["pc"], sub["gc"], sub["e"], sub["H0"], sub["lp0"]
-        building, log_u_leaf, n_sub = sub["building"], sub["log_u_leaf"], sub["n_sub"]
-        for t in (zc, pc, gc, e, H0, log_u_leaf, sub["ck_p"], sub["ck_rho"], sub["sum_acc"], sub["n_leaf"]):
-            if not (t.is_cuda and t.is_contiguous()):
-                raise RuntimeError("magi_b200: the fused NUTS path needs contiguous CUDA tensors (no CPU fallback)")
-        rho_sub = torch.zeros_like(zc)
-        logw_sub = torch.full_like(H0, -math.inf)
-        sub_z, sub_lp = zc.clone(), lp0.clone()
+        p0 = torch.empty((self.C, self.S), dtype=torch.float64, device=self.prob.device)
+        ids = chain_ids.to(torch.int64).contiguous()
+        with torch.cuda.device(self.prob.device):
+            self._lib.check(self._lib.lib().magi_b200_nuts_momentum(int(seed), Ct.c_void_p(ids.data_ptr()),
+                                                                    int(iteration), self.C, self.S,
+                                                                    Ct.c_void_p(p0.data_ptr()), self._stream()),
+                            "nuts_momentum")
+        return p0
+
+    def _tree_struct(self, tree: dict, active: Tensor):
+        import ctypes as Ct
         ptr = lambda t: Ct.c_void_p(t.data_ptr())
-        st = L.NutsSubtree(self.C, self.nD, self.D, self.P, ptr(zc), ptr(pc), ptr(gc), ptr(rho_sub), ptr(sub_z),
-                           ptr(sub_lp), ptr(logw_sub), ptr(sub["sum_acc"]), ptr(sub["n_leaf"]), ptr(building),
-                           ptr(sub["diverged"]), ptr(sub["ck_p"]), ptr(sub["ck_rho"]), ptr(e), ptr(H0))
+        for k in ("zl", "pl", "gl", "zr", "pr", "gr", "rho", "prop_z", "prop_lp", "logw", "fwd"):
+            if not (tree[k].is_cuda and tree[k].is_contiguous()):
+                raise RuntimeError("magi_b200: the fused NUTS path needs contiguous CUDA tensors (no CPU fallback)")
+        return self._lib.NutsTree(*(ptr(tree[k]) for k in ("zl", "pl", "gl", "zr", "pr", "gr", "rho", "prop_z",
+                                                           "prop_lp", "logw")), ptr(active), ptr(tree["fwd"]))
+
+    def begin(self, sub: dict, tree: dict) -> None:
+        import ctypes as Ct
+        L = self._lib
+        ptr = lambda t: Ct.c_void_p(t.data_ptr())
+        for k in ("e", "H0", "log_u_leaf", "ck_p", "ck_rho", "sum_acc", "n_leaf", "building", "diverged"):
+            if not (sub[k].is_cuda and sub[k].is_contiguous()):
+                raise RuntimeError("magi_b200: the fused NUTS path needs contiguous CUDA tensors (no CPU fallback)")
+        self._st = L.NutsSubtree(self.C, self.nD, self.D, self.P, ptr(self.zc), ptr(self.pc), ptr(self.gc),
+                                 ptr(self.rho_sub), ptr(self.sub_z), ptr(self.sub_lp), ptr(self.logw_sub),
+                                 ptr(sub["sum_acc"]), ptr(sub["n_leaf"]), ptr(sub["building"]), ptr(sub["diverged"]),
+                                 ptr(sub["ck_p"]), ptr(sub["ck_rho"]), ptr(sub["e"]), ptr(sub["H0"]))
+        self._sub = sub                                         # keeps the tensors behind the raw pointers alive
+        self.sub_lp.copy_(sub["lp0"])
+        self.logw_sub.fill_(-math.inf)
+        self._active_out = torch.zeros(self.C, dtype=torch.bool, device=self.prob.device)
+        tr = self._tree_struct(tree, self._active_out)
+        with torch.cuda.device(self.prob.device):
+            L.check(L.lib().magi_b200_nuts_subtree_begin(Ct.byref(self._st), Ct.byref(tr), self._stream()),
+                    "nuts_subtree_begin")
+
+    def build_subtree(self, sub: dict) -> None:
+        import ctypes as Ct
+        L, lib, st = self._lib, self._lib.lib(), self._st
+        building, log_u_leaf, n_sub = sub["building"], sub["log_u_leaf"], sub["n_sub"]
+        ptr = lambda t: Ct.c_void_p(t.data_ptr())
         lp, gX, gs, gt = self.out
-        with torch.cuda.device(zc.device):
-            stream = Ct.c_void_p(torch.cuda.current_stream(zc.device).cuda_stream)
+        with torch.cuda.device(self.prob.device):
+            stream = self._stream()
             for i in range(n_sub):
                 if i % sub["sync_every"] == 0 and i > 0 and not bool(building.any()):
                     break
@@ -368,4 +424,13 @@ class FusedLeafEngine:
                                                      Ct.c_void_p(log_u_leaf.data_ptr() + 8 * i), n_sub,
                                                      float(sub["max_energy_diff"]), slot_store, len(slots), arr,
                                                      stream), "nuts_leaf_post")
-        return rho_sub, logw_sub, sub_z, sub_lp, building
+
+    def merge(self, tree: dict, log_u_acc: Tensor) -> Tensor:
+        import ctypes as Ct
+        L = self._lib
+        tr = self._tree_struct(tree, self._active_out)
+        lu = log_u_acc.contiguous()
+        with torch.cuda.device(self.prob.device):
+            L.check(L.lib().magi_b200_nuts_merge(Ct.byref(self._st), Ct.byref(tr), Ct.c_void_p(lu.data_ptr()),
+                                                 self._stream()), "nuts_merge")
+        return self._active_out
