@@ -90,6 +90,13 @@ typedef struct {
 MAGI_API int magi_b200_nuts_momentum(uint64_t seed, const int64_t* chain_ids, uint32_t iteration, int C, int S,
                                      double* p0, magi_stream_t stream);
 
+/* Uniform draws of the tree builder from the same stream: ua[c,k], ub[c,k] = the two (0,1) doubles of
+ * Philox(counter = (index0 + k, chain_ids[c], iteration, purpose)), k < count.  purpose 2, index = doubling j: ua decides
+ * the direction (ua < 1/2 = forward), ub the acceptance of the completed subtree; purpose 3, index = number of the leaf
+ * within the transition: ua selects the proposal inside the subtree. */
+MAGI_API int magi_b200_nuts_uniforms(uint64_t seed, const int64_t* chain_ids, uint32_t iteration, uint32_t purpose,
+                                     uint32_t index0, int count, int C, double* ua, double* ub, magi_stream_t stream);
+
 /* Start of a doubling: (zc, pc, gc) <- the end of the tree the direction points to, rho_sub <- 0, sub_z <- zc. */
 MAGI_API int magi_b200_nuts_subtree_begin(const magi_nuts_subtree_t* st, const magi_nuts_tree_t* tree,
                                           magi_stream_t stream);

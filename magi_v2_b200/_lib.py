@@ -64,6 +64,8 @@ _SIGNATURES = {
     "magi_b200_hmc_run": (C.c_int, [C.POINTER(Problem), C.POINTER(HmcConfig)] + [C.c_void_p] * 13 +
                           [C.c_size_t, C.c_void_p]),
     "magi_b200_nuts_momentum": (C.c_int, [C.c_uint64, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "magi_b200_nuts_uniforms": (C.c_int, [C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
     "magi_b200_nuts_subtree_begin": (C.c_int, [C.POINTER(NutsSubtree), C.POINTER(NutsTree), C.c_void_p]),
     "magi_b200_nuts_merge": (C.c_int, [C.POINTER(NutsSubtree), C.POINTER(NutsTree), C.c_void_p, C.c_void_p]),
     "magi_b200_nuts_leaf_pre": (C.c_int, [C.POINTER(NutsSubtree)] + [C.c_void_p] * 5),

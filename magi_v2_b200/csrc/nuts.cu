@@ -57,7 +57,8 @@ __device__ __forceinline__ double logaddexp_d(double a, double b) {
   return m + log1p(exp(-fabs(a - b)));
 }
 
-__global__ void __launch_bounds__(kThreads) nuts_leaf_post_kernel(magi_nuts_subtree_t st,
+template <int NCHK>
+__global__ void __launch_bounds__(kThreads, NCHK <= 2 ? 4 : 2) nuts_leaf_post_kernel(magi_nuts_subtree_t st,
                                                                   const double* __restrict__ ph, Parts zn, Parts gn,
                                                                   const double* __restrict__ lp_new,
                                                                   const double* __restrict__ log_u, int64_t log_u_stride,
@@ -76,9 +77,9 @@ __global__ void __launch_bounds__(kThreads) nuts_leaf_post_kernel(magi_nuts_subt
   double* store_r = slot_store >= 0 ? st.ck_rho + ((size_t)slot_store * C + c) * S : nullptr;
 
   // acc[0] = p.p ; acc[1 + 2k] = rb_k . ck_p_k ; acc[2 + 2k] = rb_k . p
-  double acc[1 + 2 * MAGI_NUTS_MAX_CHECKS];
+  double acc[1 + 2 * NCHK];
 #pragma unroll
-  for (int q = 0; q < 1 + 2 * MAGI_NUTS_MAX_CHECKS; ++q) acc[q] = 0.0;
+  for (int q = 0; q < 1 + 2 * NCHK; ++q) acc[q] = 0.0;
 
   for (int i = threadIdx.x; i < S; i += kThreads) {
     const double g = part_load(gn, c, i, nD, D, P);
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(kThreads) nuts_leaf_post_kernel(magi_nuts_subt
     }
     acc[0] = fma(p, p, acc[0]);
 #pragma unroll
-    for (int k = 0; k < MAGI_NUTS_MAX_CHECKS; ++k) {
+    for (int k = 0; k < NCHK; ++k) {
       if (k < ck.n) {
         const size_t o = ((size_t)ck.slot[k] * C + c) * S + i;
         const double rb = r_new - st.ck_rho[o];
@@ -106,12 +107,12 @@ __global__ void __launch_bounds__(kThreads) nuts_leaf_post_kernel(magi_nuts_subt
     }
   }
 
-  __shared__ double red[kThreads / 32][1 + 2 * MAGI_NUTS_MAX_CHECKS];
+  __shared__ double red[kThreads / 32][1 + 2 * NCHK];
   __shared__ int s_take;
   const int nred = 1 + 2 * ck.n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int q = 0; q < 1 + 2 * MAGI_NUTS_MAX_CHECKS; ++q) {
+  for (int q = 0; q < 1 + 2 * NCHK; ++q) {
     if (q < nred) {
       const double v = magi_warp_sum(acc[q]);
       if (lane == 0) red[warp][q] = v;
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(kThreads) nuts_leaf_post_kernel(magi_nuts_subt
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double tot[1 + 2 * MAGI_NUTS_MAX_CHECKS];
+    double tot[1 + 2 * NCHK];
     for (int q = 0; q < nred; ++q) {
       double v = 0.0;
       for (int w = 0; w < kThreads / 32; ++w) v += red[w][q];
@@ -146,6 +147,19 @@ __global__ void __launch_bounds__(kThreads) nuts_leaf_post_kernel(magi_nuts_subt
     double* sz = st.sub_z + row;
     for (int i = threadIdx.x; i < S; i += kThreads) sz[i] = zc[i];
   }
+}
+
+__global__ void __launch_bounds__(kThreads) nuts_uniform_kernel(uint64_t seed, const int64_t* __restrict__ chain_ids,
+                                                                uint32_t iteration, uint32_t purpose, uint32_t index0,
+                                                                int count, int C, double* __restrict__ ua,
+                                                                double* __restrict__ ub) {
+  const size_t t = (size_t)blockIdx.x * kThreads + threadIdx.x;
+  if (t >= (size_t)C * count) return;
+  const int c = (int)(t / count), k = (int)(t % count);
+  const uint4 r = magi_philox(make_uint4(index0 + (uint32_t)k, (uint32_t)chain_ids[c], iteration, purpose),
+                              make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  ua[t] = magi_u53(r.x, r.y);
+  ub[t] = magi_u53(r.z, r.w);
 }
 
 __global__ void __launch_bounds__(kThreads) nuts_momentum_kernel(uint64_t seed, const int64_t* __restrict__ chain_ids,
@@ -273,8 +287,16 @@ extern "C" int magi_b200_nuts_leaf_post(const magi_nuts_subtree_t* st, const dou
   ck.n = n_checks;
   for (int k = 0; k < MAGI_NUTS_MAX_CHECKS; ++k) ck.slot[k] = k < n_checks ? check_slots[k] : 0;
   const Parts zn{Xn, sn, tn}, gn{gX, gs, gt};
-  nuts_leaf_post_kernel<<<st->C, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      *st, ph, zn, gn, lp_new, log_u, log_u_stride, max_energy_diff, slot_store, ck);
+  const cudaStream_t cs = static_cast<cudaStream_t>(stream);
+#define MAGI_POST(N) \
+  nuts_leaf_post_kernel<N><<<st->C, kThreads, 0, cs>>>(*st, ph, zn, gn, lp_new, log_u, log_u_stride, max_energy_diff, \
+                                                      slot_store, ck)
+  if (n_checks == 0) MAGI_POST(0);
+  else if (n_checks == 1) MAGI_POST(1);
+  else if (n_checks == 2) MAGI_POST(2);
+  else if (n_checks <= 4) MAGI_POST(4);
+  else MAGI_POST(MAGI_NUTS_MAX_CHECKS);
+#undef MAGI_POST
   return magi_cuda_status(cudaGetLastError());
 }
 
@@ -309,5 +331,19 @@ extern "C" int magi_b200_nuts_merge(const magi_nuts_subtree_t* st, const magi_nu
   if (int s = check_tree(tree)) return s;
   if (!log_u_acc) return -3;
   nuts_merge_kernel<<<st->C, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(*st, *tree, log_u_acc);
+  return magi_cuda_status(cudaGetLastError());
+}
+
+extern "C" int magi_b200_nuts_uniforms(uint64_t seed, const int64_t* chain_ids, uint32_t iteration, uint32_t purpose,
+                                       uint32_t index0, int count, int C, double* ua, double* ub,
+                                       magi_stream_t stream) {
+  if (!chain_ids) return -2;
+  if (count <= 0) return -6;
+  if (C <= 0) return -7;
+  if (!ua) return -8;
+  if (!ub) return -9;
+  const size_t total = (size_t)C * count;
+  nuts_uniform_kernel<<<(unsigned)((total + kThreads - 1) / kThreads), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      seed, chain_ids, iteration, purpose, index0, count, C, ua, ub);
   return magi_cuda_status(cudaGetLastError());
 }

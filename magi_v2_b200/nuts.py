@@ -168,7 +168,8 @@ def nuts_transition(z: Tensor, eps: Tensor, value_and_grad: Callable[[Tensor], T
     else:
         p0 = leaf_engine.momentum(seed, chain_ids, iteration)
     H0 = -lp0 + 0.5 * _dot(p0, p0)
-    u_dir, u_acc = rng_uniform_pairs(seed, chain_ids, iteration, RNG_NUTS_DEPTH, 0, max_tree_depth)
+    uniforms = rng_uniform_pairs if leaf_engine is None else leaf_engine.uniforms
+    u_dir, u_acc = uniforms(seed, chain_ids, iteration, RNG_NUTS_DEPTH, 0, max_tree_depth)
 
     zl, pl, gl = z.clone(), p0.clone(), g0.clone()           # leftmost / rightmost states of the tree
     zr, pr, gr = z.clone(), p0.clone(), g0.clone()
@@ -195,7 +196,7 @@ def nuts_transition(z: Tensor, eps: Tensor, value_and_grad: Callable[[Tensor], T
         fwd = u_dir[:, j] < 0.5
         e = torch.where(fwd, eps, -eps)
         n_sub = 1 << j
-        u_leaf, _ = rng_uniform_pairs(seed, chain_ids, iteration, RNG_NUTS_LEAF, n_sub - 1, n_sub)
+        u_leaf, _ = uniforms(seed, chain_ids, iteration, RNG_NUTS_LEAF, n_sub - 1, n_sub)
         sub = dict(e=e, H0=H0, lp0=lp0, building=active.clone(), log_u_leaf=torch.log(u_leaf),
                    sum_acc=sum_acc, n_leaf=n_leaf, diverged=diverged, ck_p=ck_p, ck_rho=ck_rho, n_sub=n_sub,
                    max_energy_diff=max_energy_diff, sync_every=sync_every)
@@ -369,6 +370,16 @@ class FusedLeafEngine:
                                                                     Ct.c_void_p(p0.data_ptr()), self._stream()),
                             "nuts_momentum")
         return p0
+
+    def uniforms(self, seed: int, chain_ids: Tensor, iteration: int, purpose: int, index0: int, count: int):
+        import ctypes as Ct
+        ua, ub = (torch.empty((self.C, count), dtype=torch.float64, device=self.prob.device) for _ in range(2))
+        ids = chain_ids.to(torch.int64).contiguous()
+        with torch.cuda.device(self.prob.device):
+            self._lib.check(self._lib.lib().magi_b200_nuts_uniforms(
+                int(seed), Ct.c_void_p(ids.data_ptr()), int(iteration), int(purpose), int(index0), int(count), self.C,
+                Ct.c_void_p(ua.data_ptr()), Ct.c_void_p(ub.data_ptr()), self._stream()), "nuts_uniforms")
+        return ua, ub
 
     def _tree_struct(self, tree: dict, active: Tensor):
         import ctypes as Ct
