@@ -31,7 +31,20 @@ struct FactorSmem {
 // C may alias A when N <= 64 (each 64-row strip of A is fully read before the strip is stored).
 __device__ void cta_gemm(int M, int N, int K, double alpha, const double* A, long rsA, long csA, const double* B,
                          long rsB, long csB, double beta, double* C, long ldc, FactorSmem& sm) {
+  // Thread (tx, ty) owns rows ty*4 + r and columns tx + 16*c of the 64x64 tile: the four B values of a k-step are
+  // 16 doubles apart across the half-warp (conflict-free; columns tx*4 + c were a 4-way bank conflict) and the A
+  // values are a broadcast.  The next k-chunk is fetched from global memory into registers while the current one is
+  // multiplied out of shared memory.
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  constexpr int kPer = kNB * kKC / kFT;  // 4 elements of each operand per thread and chunk
+  // element -> (k, row/col) maps of the staging loads, fastest index along the operand's unit stride
+  int ak[kPer], ai[kPer], bk[kPer], bj[kPer];
+#pragma unroll
+  for (int q = 0; q < kPer; ++q) {
+    const int e = tid + q * kFT;
+    if (csA == 1) { ak[q] = e & (kKC - 1); ai[q] = e >> 4; } else { ai[q] = e & (kNB - 1); ak[q] = e >> 6; }
+    if (csB == 1) { bj[q] = e & (kNB - 1); bk[q] = e >> 6; } else { bk[q] = e & (kKC - 1); bj[q] = e >> 4; }
+  }
   for (int m0 = 0; m0 < M; m0 += kNB) {
     for (int n0 = 0; n0 < N; n0 += kNB) {
       double acc[4][4];
@@ -39,27 +52,32 @@ __device__ void cta_gemm(int M, int N, int K, double alpha, const double* A, lon
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+      double pa[kPer], pb[kPer];
+      auto fetch = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+          const int gi = m0 + ai[q], gk = k0 + ak[q];
+          pa[q] = (gi < M && gk < K) ? A[gi * rsA + gk * csA] : 0.0;
+          const int gj = n0 + bj[q], gk2 = k0 + bk[q];
+          pb[q] = (gj < N && gk2 < K) ? B[gk2 * rsB + gj * csB] : 0.0;
+        }
+      };
+      fetch(0);
       for (int k0 = 0; k0 < K; k0 += kKC) {
 #pragma unroll
-        for (int e = tid; e < kNB * kKC; e += kFT) {
-          int kk, i;
-          if (csA == 1) { kk = e & (kKC - 1); i = e >> 4; } else { i = e & (kNB - 1); kk = e >> 6; }
-          const int gi = m0 + i, gk = k0 + kk;
-          sm.a[kk][i] = (gi < M && gk < K) ? A[gi * rsA + gk * csA] : 0.0;
-          int j;
-          if (csB == 1) { j = e & (kNB - 1); kk = e >> 6; } else { kk = e & (kKC - 1); j = e >> 4; }
-          const int gj = n0 + j;
-          const int gk2 = k0 + kk;
-          sm.b[kk][j] = (gj < N && gk2 < K) ? B[gk2 * rsB + gj * csB] : 0.0;
+        for (int q = 0; q < kPer; ++q) {
+          sm.a[ak[q]][ai[q]] = pa[q];
+          sm.b[bk[q]][bj[q]] = pb[q];
         }
         __syncthreads();
+        if (k0 + kKC < K) fetch(k0 + kKC);
 #pragma unroll
         for (int kk = 0; kk < kKC; ++kk) {
           double av[4], bv[4];
 #pragma unroll
           for (int r = 0; r < 4; ++r) av[r] = sm.a[kk][ty * 4 + r];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) bv[c] = sm.b[kk][tx * 4 + c];
+          for (int c = 0; c < 4; ++c) bv[c] = sm.b[kk][tx + 16 * c];
 #pragma unroll
           for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -73,7 +91,7 @@ __device__ void cta_gemm(int M, int N, int K, double alpha, const double* A, lon
         if (gi >= M) continue;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const int gj = n0 + tx * 4 + c;
+          const int gj = n0 + tx + 16 * c;
           if (gj >= N) continue;
           double* p = C + gi * ldc + gj;
           *p = beta == 0.0 ? alpha * acc[r][c] : fma(alpha, acc[r][c], beta * *p);
@@ -162,7 +180,7 @@ __device__ void cta_chol_inverse(double* Lf, double* Linv, double* T, int n, Fac
   }
 }
 
-__global__ void __launch_bounds__(kFT)
+__global__ void __launch_bounds__(kFT, 2)
 factor_kernel(const double* __restrict__ C, const double* __restrict__ Cp, const double* __restrict__ Cpp, int nmat,
               int n, int band, double jitter, double* __restrict__ Cinv, double* __restrict__ m,
               double* __restrict__ Kinv, double* __restrict__ Kout, int32_t* __restrict__ info, double* ws) {
