@@ -64,6 +64,44 @@ cov_build_kernel(const double* __restrict__ I, int64_t I_stride, const double* _
   }
 }
 
+// Uniform grid: the blocks are Toeplitz, kappa(|i - j| h), so a CTA evaluates the n distinct lags once into shared
+// memory (n Bessel evaluations instead of 32 x n for its 64 rows) and then only streams its rows out: the kernel
+// is bound by the 24 n^2 output bytes per matrix.  Same lag arithmetic as the general kernel -> identical values.
+constexpr int kRows = 64;
+
+__global__ void __launch_bounds__(256)
+cov_build_toeplitz_kernel(const double* __restrict__ I, int64_t I_stride, const double* __restrict__ phi1,
+                          const double* __restrict__ phi2, MaternConsts mc, int D, int n,
+                          double* __restrict__ C, double* __restrict__ Cp, double* __restrict__ Cpp) {
+  extern __shared__ double tab[];  // [3][n]: kappa, d kappa/d s (s > t), d^2 kappa / d s d t
+  const size_t bd = blockIdx.y;
+  const int b = (int)(bd / D);
+  const double* grid = I + (size_t)b * I_stride;
+  const double p1 = phi1[bd], p2 = phi2[bd];
+  const double h = (grid[n - 1] - grid[0]) / (double)(n - 1);
+  const double diagQ = mc.nu * p1 / (p2 * p2 * (mc.nu - 1.0));
+  const int r0 = blockIdx.x * kRows, r1 = min(n, r0 + kRows);
+  const int lmax = max(r1 - 1, n - 1 - r0);  // largest lag this CTA's rows reach
+  for (int l = threadIdx.x; l <= lmax; l += 256) {
+    double kap = p1, dk = 0.0, d2k = -diagQ;
+    if (l > 0) matern_lag(mc, p1, p2, fabs((double)l) * h, kap, dk, d2k);
+    tab[l] = kap;
+    tab[n + l] = dk;
+    tab[2 * n + l] = -d2k;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = r0 + warp; i < r1; i += 8) {
+    const size_t o = bd * (size_t)n * n + (size_t)i * n;
+    for (int j = lane; j < n; j += 32) {
+      const int l = i > j ? i - j : j - i;
+      if (C) C[o + j] = tab[l];
+      if (Cp) Cp[o + j] = i >= j ? tab[n + l] : -tab[n + l];
+      if (Cpp) Cpp[o + j] = tab[2 * n + l];
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int magi_b200_cov_build(const double* I, int64_t I_batch_stride, const double* phi1,
@@ -87,6 +125,13 @@ extern "C" int magi_b200_cov_build(const double* I, int64_t I_batch_stride, cons
   for (size_t off = 0; off < nmat; off += chunk) {
     const unsigned ny = (unsigned)((nmat - off) < chunk ? (nmat - off) : chunk);
     const size_t b0 = off / D;
+    if ((flags & MAGI_COV_UNIFORM_GRID) && 3 * (size_t)n * sizeof(double) <= 48 * 1024) {
+      cov_build_toeplitz_kernel<<<dim3((n + kRows - 1) / kRows, ny), 256, 3 * (size_t)n * sizeof(double), st>>>(
+          I + b0 * (size_t)I_batch_stride, I_batch_stride, phi1 + off, phi2 + off, mc, D, n,
+          C ? C + off * (size_t)n * n : nullptr, Cp ? Cp + off * (size_t)n * n : nullptr,
+          Cpp ? Cpp + off * (size_t)n * n : nullptr);
+      continue;
+    }
     cov_build_kernel<<<dim3(ntile, ny), 256, 0, st>>>(
         I + b0 * (size_t)I_batch_stride, I_batch_stride, phi1 + off, phi2 + off, mc, D, n, flags,
         C ? C + off * (size_t)n * n : nullptr, Cp ? Cp + off * (size_t)n * n : nullptr,
