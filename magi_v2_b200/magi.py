@@ -159,11 +159,14 @@ class MAGI_v2:
     # ------------------------------------------------------------------------------------------
     def predict(self, num_results: int = 1000, num_burnin_steps: int = 1000, sigma_sqs_LB=None, verbose=False,
                 n_chains: int = 1, n_leapfrog: int = 32, seed: int = 0, step_size: float = None,
-                init_jitter: float = 0.0, sampler: str = "hmc", max_tree_depth: int = 10):
+                init_jitter: float = 0.0, sampler: str = "hmc", max_tree_depth: int = 10,
+                beta_temp: Optional[float] = None):
         """magi_v2.py:286-425.  Returns the reference's result dictionary; with n_chains > 1 the sample
         arrays gain a leading chain axis.  sampler = "hmc": fixed-length trajectories, the whole chain inside the
         fused CUDA kernel; sampler = "nuts": the reference's sampler (No-U-Turn trees, `nuts.py`) with one launch
-        of the log-posterior + gradient kernel per leapfrog step."""
+        of the log-posterior + gradient kernel per leapfrog step.  beta_temp = None follows the reference's schedule
+        max(1 / log(step + 2), 0.1) (:833-835, which never returns to 1); a number fixes the temperature (1.0 = the
+        untempered posterior)."""
         if sampler not in ("hmc", "nuts"):
             raise ValueError("sampler must be 'hmc' or 'nuts'")
         torch = _require_cuda()
@@ -208,14 +211,15 @@ class MAGI_v2:
         num_adapt = int(0.8 * num_burnin_steps)                                                     # :365
         if sampler == "nuts":
             return self._predict_nuts(prob, X, s, tau, eps, da, num_results, num_burnin_steps, num_adapt, seed,
-                                      sigma_sqs_LB, max_tree_depth, verbose)
+                                      sigma_sqs_LB, max_tree_depth, verbose, beta_temp)
         if verbose:
             print("Starting HMC posterior sampling ...")
         start = time.time()
+        fbt = 0.0 if beta_temp is None else float(beta_temp)
         burn = prob.hmc_run_(X, s, tau, eps, da, n_iter=num_burnin_steps, n_leapfrog=n_leapfrog, iter0=0,
-                             num_adapt=num_adapt, seed=seed, keep_theta=False, keep_sigma=False)
+                             num_adapt=num_adapt, seed=seed, keep_theta=False, keep_sigma=False, fixed_beta_temp=fbt)
         out = prob.hmc_run_(X, s, tau, eps, da, n_iter=num_results, n_leapfrog=n_leapfrog, iter0=num_burnin_steps,
-                            num_adapt=num_adapt, seed=seed, keep_X=True)
+                            num_adapt=num_adapt, seed=seed, keep_X=True, fixed_beta_temp=fbt)
         torch.cuda.synchronize(dev)
         end = time.time()
         minutes = np.round((end - start) / 60, 2)
@@ -238,7 +242,7 @@ class MAGI_v2:
                 "minutes_elapsed": minutes}
 
     def _predict_nuts(self, prob, X, s, tau, eps, da, num_results, num_burnin_steps, num_adapt, seed, sigma_sqs_LB,
-                      max_tree_depth, verbose):
+                      max_tree_depth, verbose, beta_temp=None):
         """The reference's sampler stack (magi_v2.py:357-396): NUTS in dual averaging in the annealing wrapper."""
         import torch
         from . import nuts
@@ -250,10 +254,10 @@ class MAGI_v2:
             print("Starting NUTS posterior sampling ...")
         start = time.time()
         burn = nuts.nuts_run_(z, e, d, None, n_iter=num_burnin_steps, iter0=0, num_adapt=num_adapt, seed=seed,
-                              max_tree_depth=max_tree_depth, leaf_engine=eng)
+                              max_tree_depth=max_tree_depth, leaf_engine=eng, fixed_beta_temp=beta_temp)
         keep = torch.empty((num_results,) + tuple(z.shape), dtype=torch.float64, device=z.device)
         out = nuts.nuts_run_(z, e, d, None, n_iter=num_results, iter0=num_burnin_steps, num_adapt=num_adapt, seed=seed,
-                             max_tree_depth=max_tree_depth, leaf_engine=eng, on_sample=lambda it, zz, info: keep[it].copy_(zz))
+                             max_tree_depth=max_tree_depth, leaf_engine=eng, fixed_beta_temp=beta_temp, on_sample=lambda it, zz, info: keep[it].copy_(zz))
         torch.cuda.synchronize(z.device)
         minutes = np.round((time.time() - start) / 60, 2)
         if verbose:

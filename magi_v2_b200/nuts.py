@@ -411,30 +411,39 @@ class FusedLeafEngine:
                     "nuts_subtree_begin")
 
     def build_subtree(self, sub: dict) -> None:
+        """The leaves of one doubling.  Three raw C-ABI calls per leaf with pre-built argument objects (for one
+        dataset the loop is bound by launch latency, so the Python work per leaf is kept to the calls themselves)."""
         import ctypes as Ct
         L, lib, st = self._lib, self._lib.lib(), self._st
         building, log_u_leaf, n_sub = sub["building"], sub["log_u_leaf"], sub["n_sub"]
         ptr = lambda t: Ct.c_void_p(t.data_ptr())
         lp, gX, gs, gt = self.out
+        ws, nb = self.prob.workspace(self.R)
+        pb = self.prob.struct(self.R)
+        st_ref, pb_ref = Ct.byref(st), Ct.byref(pb)
+        p_ph, p_Xn, p_sn, p_tn, p_bt = ptr(self.ph), ptr(self.Xn), ptr(self.sn), ptr(self.tn), ptr(self.bt)
+        p_lp, p_gX, p_gs, p_gt, p_ws = ptr(lp), ptr(gX), ptr(gs), ptr(gt), (ptr(ws) if ws is not None else None)
+        lu0, med, sync_every = log_u_leaf.data_ptr(), float(sub["max_energy_diff"]), sub["sync_every"]
+        pre, evalf, post = lib.magi_b200_nuts_leaf_pre, lib.magi_b200_logpost_grad, lib.magi_b200_nuts_leaf_post
+        no_slots = (Ct.c_int * 1)(0)
         with torch.cuda.device(self.prob.device):
             stream = self._stream()
             for i in range(n_sub):
-                if i % sub["sync_every"] == 0 and i > 0 and not bool(building.any()):
+                if i % sync_every == 0 and i > 0 and not bool(building.any()):
                     break
-                L.check(lib.magi_b200_nuts_leaf_pre(Ct.byref(st), ptr(self.ph), ptr(self.Xn), ptr(self.sn),
-                                                    ptr(self.tn), stream), "nuts_leaf_pre")
-                self.prob.logpost_grad(self.Xn, self.sn, self.tn, self.bt, out=self.out)
-                slot_store = bin(i).count("1") if (i % 2 == 0 and n_sub > 1) else -1
-                slots = []
-                if i % 2 == 1:
+                rc = pre(st_ref, p_ph, p_Xn, p_sn, p_tn, stream)
+                rc = rc or evalf(pb_ref, p_Xn, p_sn, p_tn, p_bt, p_lp, p_gX, p_gs, p_gt, p_ws, nb, stream)
+                if i & 1:
                     t = (~i & (i + 1)).bit_length() - 1
                     slots = [bin(i - (1 << k) + 1).count("1") for k in range(1, t + 1)]
-                arr = (Ct.c_int * max(len(slots), 1))(*slots)
-                L.check(lib.magi_b200_nuts_leaf_post(Ct.byref(st), ptr(self.ph), ptr(self.Xn), ptr(self.sn),
-                                                     ptr(self.tn), ptr(lp), ptr(gX), ptr(gs), ptr(gt),
-                                                     Ct.c_void_p(log_u_leaf.data_ptr() + 8 * i), n_sub,
-                                                     float(sub["max_energy_diff"]), slot_store, len(slots), arr,
-                                                     stream), "nuts_leaf_post")
+                    arr, slot_store = (Ct.c_int * t)(*slots), -1
+                else:
+                    t, arr = 0, no_slots
+                    slot_store = bin(i).count("1") if n_sub > 1 else -1
+                rc = rc or post(st_ref, p_ph, p_Xn, p_sn, p_tn, p_lp, p_gX, p_gs, p_gt, Ct.c_void_p(lu0 + 8 * i), n_sub,
+                                med, slot_store, t, arr, stream)
+                if rc:
+                    L.check(rc, "nuts leaf (leaf_pre / logpost_grad / leaf_post)")
 
     def merge(self, tree: dict, log_u_acc: Tensor) -> Tensor:
         import ctypes as Ct
