@@ -29,8 +29,16 @@ struct FactorSmem {
 // C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C   (all 256 threads; C row-major with ldc).
 // op(A)(i,k) = A[i*rsA + k*csA], op(B)(k,j) = B[k*rsB + j*csB]; one of each stride pair is 1.
 // C may alias A when N <= 64 (each 64-row strip of A is fully read before the strip is stored).
+// Structure flags: the operands of the big products are triangular or the result is symmetric, and the tile loop
+// skips what is known to be zero / redundant (the skipped terms are exact zeros, so the values do not change):
+//   kGemmALowerT : op(A)(i,k) = 0 for k < i   (A = L^T of a lower-triangular L)      -> k starts at the tile's m0
+//   kGemmALower  : op(A)(i,k) = 0 for k > i   (A lower-triangular)                   -> k ends at m0 + 64
+//   kGemmBLower  : op(B)(k,j) = 0 for k < j   (B lower-triangular)                   -> k starts at n0
+//   kGemmSymOut  : the result is symmetric (M == N): only tiles with n0 <= m0 are computed, the others mirrored
+constexpr int kGemmALowerT = 1, kGemmALower = 2, kGemmBLower = 4, kGemmSymOut = 8;
+
 __device__ void cta_gemm(int M, int N, int K, double alpha, const double* A, long rsA, long csA, const double* B,
-                         long rsB, long csB, double beta, double* C, long ldc, FactorSmem& sm) {
+                         long rsB, long csB, double beta, double* C, long ldc, FactorSmem& sm, int flags = 0) {
   // Thread (tx, ty) owns rows ty*4 + r and columns tx + 16*c of the 64x64 tile: the four B values of a k-step are
   // 16 doubles apart across the half-warp (conflict-free; columns tx*4 + c were a 4-way bank conflict) and the A
   // values are a broadcast.  The next k-chunk is fetched from global memory into registers while the current one is
@@ -47,6 +55,11 @@ __device__ void cta_gemm(int M, int N, int K, double alpha, const double* A, lon
   }
   for (int m0 = 0; m0 < M; m0 += kNB) {
     for (int n0 = 0; n0 < N; n0 += kNB) {
+      if ((flags & kGemmSymOut) && n0 > m0) break;
+      int kbeg = 0, kend = K;
+      if (flags & kGemmALowerT) kbeg = max(kbeg, m0);
+      if (flags & kGemmBLower) kbeg = max(kbeg, n0);
+      if (flags & kGemmALower) kend = min(kend, m0 + kNB);
       double acc[4][4];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
@@ -62,15 +75,15 @@ __device__ void cta_gemm(int M, int N, int K, double alpha, const double* A, lon
           pb[q] = (gj < N && gk2 < K) ? B[gk2 * rsB + gj * csB] : 0.0;
         }
       };
-      fetch(0);
-      for (int k0 = 0; k0 < K; k0 += kKC) {
+      fetch(kbeg);
+      for (int k0 = kbeg; k0 < kend; k0 += kKC) {
 #pragma unroll
         for (int q = 0; q < kPer; ++q) {
           sm.a[ak[q]][ai[q]] = pa[q];
           sm.b[bk[q]][bj[q]] = pb[q];
         }
         __syncthreads();
-        if (k0 + kKC < K) fetch(k0 + kKC);
+        if (k0 + kKC < kend) fetch(k0 + kKC);
 #pragma unroll
         for (int kk = 0; kk < kKC; ++kk) {
           double av[4], bv[4];
@@ -94,7 +107,9 @@ __device__ void cta_gemm(int M, int N, int K, double alpha, const double* A, lon
           const int gj = n0 + tx + 16 * c;
           if (gj >= N) continue;
           double* p = C + gi * ldc + gj;
-          *p = beta == 0.0 ? alpha * acc[r][c] : fma(alpha, acc[r][c], beta * *p);
+          const double v = beta == 0.0 ? alpha * acc[r][c] : fma(alpha, acc[r][c], beta * *p);
+          *p = v;
+          if ((flags & kGemmSymOut) && n0 < m0) C[gj * ldc + gi] = v;
         }
       }
     }
@@ -175,7 +190,7 @@ __device__ void cta_chol_inverse(double* Lf, double* Linv, double* T, int n, Fac
   //   Linv[i, 0:c0] = -Linv_ii * ( L[i, 0:c0] * Linv[0:c0, 0:c0] )
   for (int i = 1; i < nblk; ++i) {
     const int c0 = i * kNB, nb = min(kNB, n - c0);
-    cta_gemm(nb, c0, c0, 1.0, Lf + (size_t)c0 * n, n, 1, Linv, n, 1, 0.0, T, n, sm);
+    cta_gemm(nb, c0, c0, 1.0, Lf + (size_t)c0 * n, n, 1, Linv, n, 1, 0.0, T, n, sm, kGemmBLower);
     cta_gemm(nb, c0, nb, -1.0, Linv + (size_t)c0 * n + c0, n, 1, T, n, 1, 0.0, Linv + (size_t)c0 * n, n, sm);
   }
 }
@@ -210,16 +225,16 @@ factor_kernel(const double* __restrict__ C, const double* __restrict__ Cp, const
     __syncthreads();
     if (tid == 0) sm.info = 0;
     // C^-1 = Linv^T Linv
-    cta_gemm(n, n, n, 1.0, Linv, 1, n, Linv, n, 1, 0.0, ci, n, sm);
+    cta_gemm(n, n, n, 1.0, Linv, 1, n, Linv, n, 1, 0.0, ci, n, sm, kGemmALowerT | kGemmBLower | kGemmSymOut);
     // W = L^-1 C'^T.  m and K are formed from W rather than through the explicit inverse:
     //   m = C' C^-1 = W^T L^-1 ,   K = C'' - C' C^-1 C'^T = C'' - W^T W
     // -- the subtraction of a Gram matrix keeps K symmetric positive definite to rounding, where
     // C'' - (C' C^-1) C'^T loses eps * cond(C) (non-PD pivots at n = 1281 without jitter).
-    cta_gemm(n, n, n, 1.0, Linv, n, 1, cp, 1, n, 0.0, W, n, sm);
-    cta_gemm(n, n, n, 1.0, W, 1, n, Linv, n, 1, 0.0, mo, n, sm);
+    cta_gemm(n, n, n, 1.0, Linv, n, 1, cp, 1, n, 0.0, W, n, sm, kGemmALower);
+    cta_gemm(n, n, n, 1.0, W, 1, n, Linv, n, 1, 0.0, mo, n, sm, kGemmBLower);
     for (size_t e = tid; e < nn; e += kFT) ki[e] = cpp[e];
     __syncthreads();
-    cta_gemm(n, n, n, -1.0, W, 1, n, W, n, 1, 1.0, ki, n, sm);
+    cta_gemm(n, n, n, -1.0, W, 1, n, W, n, 1, 1.0, ki, n, sm, kGemmSymOut);
     // symmetrise K (the factorisation reads the lower triangle), keep a copy if asked for
     for (size_t e = tid; e < nn; e += kFT) {
       const int i = (int)(e / n), j = (int)(e % n);
@@ -232,7 +247,7 @@ factor_kernel(const double* __restrict__ C, const double* __restrict__ Cp, const
     __syncthreads();
     cta_chol_inverse(Lf, Linv, T, n, sm);
     const int infoK = sm.info;
-    cta_gemm(n, n, n, 1.0, Linv, 1, n, Linv, n, 1, 0.0, ki, n, sm);
+    cta_gemm(n, n, n, 1.0, Linv, 1, n, Linv, n, 1, 0.0, ki, n, sm, kGemmALowerT | kGemmBLower | kGemmSymOut);
     if (band >= 0) {
       for (size_t e = tid; e < nn; e += kFT) {
         const int i = (int)(e / n), j = (int)(e % n);
