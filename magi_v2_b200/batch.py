@@ -62,13 +62,18 @@ class MagiBatch:
         self.sigma_sqs_LB = (0.01 * self.Xhat_init.std(axis=1)) ** 2                      # :299-300
         self.prob, info = synth.device_problem(self.model.name, c["I"], self.phi1s, self.phi2s, c["y"], c["mask"],
                                                c["N_ds"], c["beta"], c["mu"], self.sigma_sqs_LB, self.BANDSIZE,
-                                               self.device, nu=self.NU, uniform_grid=False, keep_matrices=True)
+                                               self.device, nu=self.NU, uniform_grid=self._uniform_grid(),
+                                               keep_matrices=True)
         self.factor_info = info.cpu().numpy()
         if np.any(self.factor_info != 0):
             bad = np.argwhere(self.factor_info != 0)[:5].tolist()
             raise np.linalg.LinAlgError(f"covariance not positive definite for (dataset, component) {bad}")
         self.thetas_init = self._fit_thetas_init()
         return self
+
+    def _uniform_grid(self) -> bool:
+        steps = np.diff(np.asarray(self.I, dtype=np.float64))
+        return bool(np.allclose(steps, steps[0], rtol=1e-10, atol=0.0))
 
     def _fit_thetas_init(self, iters: int = 10000, lr: float = 0.01):
         """magi_v2.py:132-179 batched: Adam (lr 0.01, 10 000 steps from theta = 1) on t2(theta), which is

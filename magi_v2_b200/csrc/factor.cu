@@ -132,10 +132,9 @@ __device__ void smem_potrf_trtri(FactorSmem& sm, int nb, int base) {
     for (int i = j + 1 + tid; i < nb; i += kFT) sm.d[i][j] *= inv;
     __syncthreads();
     // trailing update of the lower triangle: d[i][k] -= d[i][j] d[k][j],  j < k <= i < nb
-    const int rem = nb - j - 1;
-    for (int e = tid; e < rem * rem; e += kFT) {
-      const int i = j + 1 + e / rem, k = j + 1 + e % rem;
-      if (k <= i) sm.d[i][k] = fma(-sm.d[i][j], sm.d[k][j], sm.d[i][k]);
+    for (int i = j + 1 + (tid >> 4); i < nb; i += kFT / 16) {
+      const double dij = sm.d[i][j];
+      for (int k = j + 1 + (tid & 15); k <= i; k += 16) sm.d[i][k] = fma(-dij, sm.d[k][j], sm.d[i][k]);
     }
     __syncthreads();
   }
@@ -154,12 +153,13 @@ __device__ void smem_potrf_trtri(FactorSmem& sm, int nb, int base) {
   __syncthreads();
 }
 
-// A (n x n, lower triangle used) -> L (in Lf, lower; upper part left as is) and Linv = L^-1 (full
-// n x n, upper part zero).  T: scratch kNB x n.  All in global memory.
+// A (n x n, lower triangle used) -> L (in Lf, lower; upper part left as is) and Linv = L^-1 (block lower
+// triangle of an n x n array; see below).  T: scratch kNB x n.  All in global memory.
 __device__ void cta_chol_inverse(double* Lf, double* Linv, double* T, int n, FactorSmem& sm) {
+  // Linv is written block row by block row: the diagonal blocks in full (zeros above the diagonal), the blocks left
+  // of them by the triangular inverse below; the blocks right of the diagonal are never written NOR read (every
+  // product that takes Linv as an operand carries the matching kGemm*Lower flag).
   const int tid = threadIdx.x;
-  for (size_t e = tid; e < (size_t)n * n; e += kFT) Linv[e] = 0.0;
-  __syncthreads();
   const int nblk = (n + kNB - 1) / kNB;
   for (int k = 0; k < nblk; ++k) {
     const int c0 = k * kNB, nb = min(kNB, n - c0);
@@ -174,10 +174,8 @@ __device__ void cta_chol_inverse(double* Lf, double* Linv, double* T, int n, Fac
     smem_potrf_trtri(sm, nb, c0);
     for (int e = tid; e < nb * nb; e += kFT) {
       const int i = e / nb, j = e % nb;
-      if (j <= i) {
-        Lf[(size_t)(c0 + i) * n + c0 + j] = sm.d[i][j];
-        Linv[(size_t)(c0 + i) * n + c0 + j] = sm.di[i][j];
-      }
+      if (j <= i) Lf[(size_t)(c0 + i) * n + c0 + j] = sm.d[i][j];
+      Linv[(size_t)(c0 + i) * n + c0 + j] = sm.di[i][j];
     }
     __syncthreads();
     // panel below the diagonal block:  L[r, blk] = A[r, blk] * inv(L_kk)^T   (in place, N = nb <= 64)

@@ -31,7 +31,7 @@ def fourier_prior(X_filled: np.ndarray):
     return mu_phi2, (1 - mu_phi2) / 3
 
 
-def objective_and_grad(v, grid, dt, xc, loc, scale):
+def objective_and_grad(v, grid, dt, xc, loc, scale, uniform_grid: bool = False):
     """Per (dataset, component): log N(x; mu 1, phi1 R(phi2) + (sigma^2 + jitter) I) + the three normal prior
     terms, as a function of the softplus pre-activations v [3,B,D] = (phi1, phi2, sigma^2), and the gradient of
     its NEGATIVE (the Adam loss) with respect to v.  Closed form:
@@ -43,7 +43,7 @@ def objective_and_grad(v, grid, dt, xc, loc, scale):
     eye = torch.eye(n, dtype=torch.float64, device=v.device)
     h = torch.nn.functional.softplus(v)
     phi1, phi2, sig2 = h[0].contiguous(), h[1].contiguous(), h[2]
-    C, Cp, _ = ops.cov_build(grid, phi1, phi2, NU, False)
+    C, Cp, _ = ops.cov_build(grid, phi1, phi2, NU, uniform_grid)
     S = C + (sig2 + JITTER)[..., None, None] * eye
     L, info = torch.linalg.cholesky_ex(S)
     Sinv = torch.cholesky_inverse(L)
@@ -81,6 +81,8 @@ def fit_kernel_hparams(I: np.ndarray, X_filled: np.ndarray, device="cuda:0", num
     scale = T(np.stack([np.full((B, D), 1000.0 * np.sqrt(D)), sd_phi2 * np.sqrt(D),
                         np.full((B, D), 1000.0 * np.sqrt(D))]))
     grid = T(I)
+    steps = np.diff(np.asarray(I, dtype=np.float64))
+    uniform = bool(np.allclose(steps, steps[0], rtol=1e-10, atol=0.0))          # Toeplitz kernel of cov_build
     dt = grid[:, None] - grid[None, :]                                         # s_i - s_j
     x = T(np.transpose(X_filled, (0, 2, 1)))                                    # [B,D,n]
     xc = x - x.mean(dim=-1, keepdim=True)                                       # mean_fn = column mean (:559, :589)
@@ -88,7 +90,7 @@ def fit_kernel_hparams(I: np.ndarray, X_filled: np.ndarray, device="cuda:0", num
     m2 = torch.zeros_like(v)
     b1, b2, eps = 0.9, 0.999, 1e-7                                              # tf_keras Adam defaults
     for t in range(1, num_iters + 1):
-        obj, g = objective_and_grad(v, grid, dt, xc, loc, scale)
+        obj, g = objective_and_grad(v, grid, dt, xc, loc, scale, uniform)
         m1 = b1 * m1 + (1 - b1) * g
         m2 = b2 * m2 + (1 - b2) * g * g
         lr_t = lr * np.sqrt(1 - b2 ** t) / (1 - b1 ** t)

@@ -101,3 +101,20 @@ def test_nuts_samples_a_gaussian():
     m, v = s.mean((0, 1)), s.var((0, 1))
     assert torch.all((m - mu).abs() < 0.08 * sd * 2), (m - mu)
     assert torch.all((v / sd ** 2 - 1).abs() < 0.08), v / sd ** 2
+
+
+def test_results_do_not_depend_on_how_chains_are_sharded():
+    """The draws are keyed by the GLOBAL chain id (csrc/rng.cuh counters), so running all chains at once or as two
+    shards (as two ranks would) gives the same states and the same trees."""
+    S, C = 6, 10
+    vg_np, vg_t = _target(S, 4)
+    z0 = torch.as_tensor(np.random.default_rng(1).standard_normal((C, S)) * 0.3)
+    run = lambda z, ids: nuts.nuts_run_(z, torch.full((len(ids),), 0.2, dtype=torch.float64),
+                                        torch.zeros((len(ids), 4), dtype=torch.float64), lambda zz, bt: vg_t(zz),
+                                        n_iter=4, fixed_beta_temp=1.0, seed=11, chain_ids=ids, max_tree_depth=5)
+    ids = torch.arange(40, 40 + C, dtype=torch.int64)
+    za = z0.clone(); oa = run(za, ids)
+    zb1, zb2 = z0[:4].clone(), z0[4:].clone()
+    ob1, ob2 = run(zb1, ids[:4]), run(zb2, ids[4:])
+    assert torch.equal(za, torch.cat([zb1, zb2]))
+    assert torch.equal(oa["n_leapfrog"], torch.cat([ob1["n_leapfrog"], ob2["n_leapfrog"]], dim=1))
