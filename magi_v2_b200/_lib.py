@@ -63,6 +63,8 @@ _SIGNATURES = {
                                                                                 C.c_size_t, C.c_void_p]),
     "magi_b200_hmc_run": (C.c_int, [C.POINTER(Problem), C.POINTER(HmcConfig)] + [C.c_void_p] * 13 +
                           [C.c_size_t, C.c_void_p]),
+    "magi_b200_logpost_grad_wide_workspace_bytes": (C.c_size_t, [C.POINTER(Problem)]),
+    "magi_b200_logpost_grad_wide": (C.c_int, [C.POINTER(Problem)] + [C.c_void_p] * 9 + [C.c_size_t, C.c_void_p]),
     "magi_b200_nuts_momentum": (C.c_int, [C.c_uint64, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "magi_b200_nuts_uniforms": (C.c_int, [C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1,0 +1,429 @@
+// Log-posterior + gradient for few datasets: the rows of every component's matrices spread over the grid
+// (include/magi_b200_wide.h).  Replaces magi_v2.py:308-348 + TF autodiff exactly like posterior_core.cuh does;
+// formulas as SURVEY.md A.2 / A.3 with the packed symmetric forms S_C = sym(C^-1), S_K = sym(K^-1):
+//   u = S_C x_c, v = m x_c, r = f(X, theta) - v, q = S_K r, t1 = x_c.u, t2 = r.q
+//   dX_d = 2 u_d + sum_d' (d f_d'/d x_d) 2 q_d' - 2 (m^T q)_d          (then / beta, + 2 e / sigma^2, * -beta_temp / 2)
+// One CTA = `rbpc` 8-row blocks of one (dataset, chain group of 8, component); its 8 warps split the tile columns of a
+// block row, each warp contracting 8x8 matrix tiles with the chain group's vectors on the FP64 tensor cores
+// (mma.sync.m8n8k4: A = half a tile, coalesced 256 B per warp load, also for the transposed pass; B = 4 x 8 slice of
+// the vector array in shared memory, conflict-free), then a cross-warp reduction.  HBM-bound: every matrix byte is
+// read once per pass by exactly one warp.
+#include "common.cuh"
+#include "ode_models.cuh"
+#include "../../include/magi_b200_wide.h"
+
+namespace {
+
+constexpr int kW = 8, kT = 32 * kW, kCh = 8;
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+struct Geo {
+  int np, nblk, kb, rbpc, nchunk, G;  // padded n, 8-row blocks, band in blocks (<0: dense), block rows per CTA, CTAs per column of the grid, chain groups
+  size_t per_bg;                      // workspace doubles per (dataset, chain group)
+};
+
+__host__ __device__ inline size_t off_R(const Geo&, int) { return 0; }
+__host__ __device__ inline size_t off_Q(const Geo& g, int D) { return (size_t)D * g.np * kCh; }
+__host__ __device__ inline size_t off_t1(const Geo& g, int D) { return 2 * (size_t)D * g.np * kCh; }
+__host__ __device__ inline size_t off_t2(const Geo& g, int D) { return off_t1(g, D) + (size_t)D * g.nchunk * kCh; }
+__host__ __device__ inline size_t off_sse(const Geo& g, int D) { return off_t2(g, D) + (size_t)D * g.nchunk * kCh; }
+__host__ __device__ inline size_t off_th(const Geo& g, int D) { return off_sse(g, D) + (size_t)D * g.nchunk * kCh; }
+
+Geo make_geo(const magi_problem_t* pb, int sms) {
+  Geo g;
+  g.np = magi_pad8(pb->n);
+  g.nblk = g.np / 8;
+  g.kb = pb->band < 0 ? -1 : (pb->band + 7) >> 3;
+  g.G = (pb->R + kCh - 1) / kCh;
+  const long ctas1 = (long)g.nblk * pb->D * pb->B * g.G;       // with one block row per CTA
+  long r = ctas1 / (4L * sms);
+  g.rbpc = (int)(r < 1 ? 1 : (r > 8 ? 8 : r));
+  g.nchunk = (g.nblk + g.rbpc - 1) / g.rbpc;
+  g.per_bg = off_th(g, pb->D) + (size_t)g.nchunk * pb->P * kCh;
+  return g;
+}
+
+__device__ __forceinline__ void jrange(const Geo& g, int I, int& lo, int& hi) {
+  lo = 0;
+  hi = g.nblk - 1;
+  if (g.kb >= 0) {
+    lo = max(lo, I - g.kb);
+    hi = min(hi, I + g.kb);
+  }
+}
+
+// cross-warp sum of NV values per lane; result valid in warp 0
+template <int NV>
+__device__ __forceinline__ void cta_reduce(double (&v)[NV], double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();  // red free (previous block row consumed)
+#pragma unroll
+  for (int q = 0; q < NV; ++q) red[(warp * NV + q) * 32 + lane] = v[q];
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < kW; ++w) s += red[(w * NV + q) * 32 + lane];
+      v[q] = s;
+    }
+  }
+}
+
+// sum over the 8 lanes that share (lane & 3), i.e. over the rows of a block row; result in lanes 0..3
+__device__ __forceinline__ double rows_sum(double v) {
+  v += magi_shfl_xor(v, 4);
+  v += magi_shfl_xor(v, 8);
+  v += magi_shfl_xor(v, 16);
+  return v;
+}
+
+struct Args {
+  magi_problem_t pb;
+  Geo g;
+  const double* X;
+  const double* sig_pre;
+  const double* th_pre;
+  const double* beta_temp;
+  double* lp;
+  double* gX;
+  double* gsig;
+  double* gth;
+  double* ws;
+};
+
+// ---- pass 1: u = S_C x_c, v = m x_c, r = f - v, t1 ------------------------------------------------------------
+template <class M>
+__global__ void __launch_bounds__(kT) wide_pass1(Args a) {
+  extern __shared__ double sm[];
+  constexpr int D = M::D, P = M::P;
+  const Geo& g = a.g;
+  double* vs = sm;                          // [np][8]
+  double* red = vs + (size_t)g.np * kCh;    // [kW][4][32]
+  double* ths = red + kW * 4 * 32;          // [8][P]
+  const int chunk = blockIdx.x, d = blockIdx.y, bg = blockIdx.z, b = bg / g.G, grp = bg % g.G;
+  const int n = a.pb.n, R = a.pb.R, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double mu_d = a.pb.mu[b * D + d];
+  for (int e = tid; e < g.np * kCh; e += kT) {
+    const int j = e >> 3, ch = e & 7, r = grp * kCh + ch;
+    vs[e] = (j < n && r < R) ? a.X[(((size_t)b * R + r) * n + j) * D + d] - mu_d : 0.0;
+  }
+  for (int e = tid; e < kCh * P; e += kT) {
+    const int ch = e / P, k = e % P, r = grp * kCh + ch;
+    ths[e] = r < R ? magi_softplus(a.th_pre[((size_t)b * R + r) * P + k]) : 1.0;
+  }
+  const double* matC = static_cast<const double*>(a.pb.packed) + ((size_t)(b * D + d) * 3 + 0) * g.np * g.np;
+  const double* matM = matC + (size_t)g.np * g.np;
+  double* wsb = a.ws + (size_t)bg * g.per_bg;
+  double* Rr = wsb + off_R(g, D);
+  double t1acc[2] = {0.0, 0.0};
+  __syncthreads();
+  const int I1 = min(g.nblk, (chunk + 1) * g.rbpc);
+  for (int I = chunk * g.rbpc; I < I1; ++I) {
+    int lo, hi;
+    jrange(g, I, lo, hi);
+    double c[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 2
+    for (int J = lo + warp; J <= hi; J += kW) {
+      const size_t t = ((size_t)I * g.nblk + J) * 64 + (lane >> 2) * 8 + (lane & 3);
+      const double a0 = matC[t], a1 = matC[t + 4], m0 = matM[t], m1 = matM[t + 4];
+      const double b0 = vs[(J * 8 + (lane & 3)) * 8 + (lane >> 2)], b1 = vs[(J * 8 + 4 + (lane & 3)) * 8 + (lane >> 2)];
+      dmma(c[0], c[1], a0, b0);
+      dmma(c[0], c[1], a1, b1);
+      dmma(c[2], c[3], m0, b0);
+      dmma(c[2], c[3], m1, b1);
+    }
+    cta_reduce<4>(c, red);
+    if (warp == 0) {
+      const int i = I * 8 + (lane >> 2);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ch = 2 * (lane & 3) + h, r = grp * kCh + ch;
+        double rv = 0.0;
+        if (i < n && r < R) {
+          const double* xp = a.X + (((size_t)b * R + r) * n + i) * D;
+          double x[D], fo[D];
+#pragma unroll
+          for (int dd = 0; dd < D; ++dd) x[dd] = xp[dd];
+          M::f(x, ths + ch * P, fo);
+          double fd = 0.0;
+#pragma unroll
+          for (int dd = 0; dd < D; ++dd) fd = dd == d ? fo[dd] : fd;
+          rv = fd - c[2 + h];
+          a.gX[(((size_t)b * R + r) * n + i) * D + d] = 2.0 * c[h];   // scratch: 2 u, finished in pass 3
+          t1acc[h] = fma(vs[i * 8 + ch], c[h], t1acc[h]);
+        }
+        Rr[((size_t)d * g.np + i) * kCh + ch] = rv;
+      }
+    }
+  }
+  if (warp == 0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const double s = rows_sum(t1acc[h]);
+      if (lane < 4) wsb[off_t1(g, D) + ((size_t)d * g.nchunk + chunk) * kCh + 2 * lane + h] = s;
+    }
+  }
+}
+
+// ---- pass 2: q = S_K r, t2 ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kT) wide_pass2(Args a, int D) {
+  extern __shared__ double sm[];
+  const Geo& g = a.g;
+  double* vs = sm;
+  double* red = vs + (size_t)g.np * kCh;
+  const int chunk = blockIdx.x, d = blockIdx.y, bg = blockIdx.z, b = bg / g.G;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* wsb = a.ws + (size_t)bg * g.per_bg;
+  const double* Rr = wsb + off_R(g, D) + (size_t)d * g.np * kCh;
+  double* Q = wsb + off_Q(g, D) + (size_t)d * g.np * kCh;
+  for (int e = tid; e < g.np * kCh; e += kT) vs[e] = Rr[e];
+  const double* matK = static_cast<const double*>(a.pb.packed) + ((size_t)(b * D + d) * 3 + 2) * g.np * g.np;
+  double t2acc[2] = {0.0, 0.0};
+  __syncthreads();
+  const int I1 = min(g.nblk, (chunk + 1) * g.rbpc);
+  for (int I = chunk * g.rbpc; I < I1; ++I) {
+    int lo, hi;
+    jrange(g, I, lo, hi);
+    double c[2] = {0.0, 0.0};
+#pragma unroll 4
+    for (int J = lo + warp; J <= hi; J += kW) {
+      const size_t t = ((size_t)I * g.nblk + J) * 64 + (lane >> 2) * 8 + (lane & 3);
+      const double a0 = matK[t], a1 = matK[t + 4];
+      dmma(c[0], c[1], a0, vs[(J * 8 + (lane & 3)) * 8 + (lane >> 2)]);
+      dmma(c[0], c[1], a1, vs[(J * 8 + 4 + (lane & 3)) * 8 + (lane >> 2)]);
+    }
+    cta_reduce<2>(c, red);
+    if (warp == 0) {
+      const int i = I * 8 + (lane >> 2);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ch = 2 * (lane & 3) + h;
+        Q[(size_t)i * kCh + ch] = c[h];      // rows >= n: zero tiles times zero r -> 0
+        t2acc[h] = fma(vs[i * 8 + ch], c[h], t2acc[h]);
+      }
+    }
+  }
+  if (warp == 0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const double s = rows_sum(t2acc[h]);
+      if (lane < 4) wsb[off_t2(g, D) + ((size_t)d * g.nchunk + chunk) * kCh + 2 * lane + h] = s;
+    }
+  }
+}
+
+// ---- pass 3: m^T q and the point-wise assembly of dX; SSE and d/d theta partial sums -------------------------------
+template <class M>
+__global__ void __launch_bounds__(kT) wide_pass3(Args a) {
+  extern __shared__ double sm[];
+  constexpr int D = M::D, P = M::P;
+  const Geo& g = a.g;
+  double* vs = sm;
+  double* red = vs + (size_t)g.np * kCh;
+  double* ths = red + kW * 4 * 32;          // [8][P]
+  const int chunk = blockIdx.x, d = blockIdx.y, bg = blockIdx.z, b = bg / g.G, grp = bg % g.G;
+  const int n = a.pb.n, R = a.pb.R, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* wsb = a.ws + (size_t)bg * g.per_bg;
+  const double* Qall = wsb + off_Q(g, D);
+  for (int e = tid; e < g.np * kCh; e += kT) vs[e] = Qall[(size_t)d * g.np * kCh + e];
+  for (int e = tid; e < kCh * P; e += kT) {
+    const int ch = e / P, k = e % P, r = grp * kCh + ch;
+    ths[e] = r < R ? magi_softplus(a.th_pre[((size_t)b * R + r) * P + k]) : 1.0;
+  }
+  const double* matM = static_cast<const double*>(a.pb.packed) + ((size_t)(b * D + d) * 3 + 1) * g.np * g.np;
+  const double inv_beta = 1.0 / a.pb.beta[b];
+  double sse[2] = {0.0, 0.0}, tha[2][P];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < P; ++k) tha[h][k] = 0.0;
+  double bt[2], isig2[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = grp * kCh + 2 * (lane & 3) + h;
+    bt[h] = r < R ? a.beta_temp[(size_t)b * R + r] : 0.0;
+    isig2[h] = r < R ? 1.0 / (magi_softplus(a.sig_pre[((size_t)b * R + r) * D + d]) + a.pb.LB[b * D + d]) : 0.0;
+  }
+  __syncthreads();
+  const int I1 = min(g.nblk, (chunk + 1) * g.rbpc);
+  for (int I = chunk * g.rbpc; I < I1; ++I) {
+    int lo, hi;
+    jrange(g, I, lo, hi);
+    double c[2] = {0.0, 0.0};
+#pragma unroll 4
+    for (int J = lo + warp; J <= hi; J += kW) {
+      // (m^T)(I, J) = tile (J, I) transposed: A[row][k] = tile[k][row]
+      const size_t t = ((size_t)J * g.nblk + I) * 64 + (lane & 3) * 8 + (lane >> 2);
+      const double a0 = matM[t], a1 = matM[t + 32];
+      dmma(c[0], c[1], a0, vs[(J * 8 + (lane & 3)) * 8 + (lane >> 2)]);
+      dmma(c[0], c[1], a1, vs[(J * 8 + 4 + (lane & 3)) * 8 + (lane >> 2)]);
+    }
+    cta_reduce<2>(c, red);
+    if (warp == 0) {
+      const int i = I * 8 + (lane >> 2);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ch = 2 * (lane & 3) + h, r = grp * kCh + ch;
+        if (i < n && r < R) {
+          const size_t xo = (((size_t)b * R + r) * n + i) * D;
+          double x[D], gq[D], vx[D], vth[P];
+#pragma unroll
+          for (int dd = 0; dd < D; ++dd) {
+            x[dd] = a.X[xo + dd];
+            gq[dd] = 2.0 * Qall[((size_t)dd * g.np + i) * kCh + ch];
+          }
+          M::vjp(x, ths + ch * P, gq, vx, vth);
+          double xd = 0.0, vxd = 0.0;
+#pragma unroll
+          for (int dd = 0; dd < D; ++dd) {
+            xd = dd == d ? x[dd] : xd;
+            vxd = dd == d ? vx[dd] : vxd;
+          }
+          const double prior = a.gX[xo + d] + vxd - 2.0 * c[h];
+          const size_t yo = ((size_t)b * n + i) * D + d;
+          const double e = a.pb.mask[yo] ? xd - a.pb.y[yo] : 0.0;
+          a.gX[xo + d] = bt[h] * -0.5 * (prior * inv_beta + 2.0 * e * isig2[h]);
+          sse[h] = fma(e, e, sse[h]);
+          if (d == 0) {
+#pragma unroll
+            for (int k = 0; k < P; ++k) tha[h][k] += vth[k];
+          }
+        }
+      }
+    }
+  }
+  if (warp == 0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const double s = rows_sum(sse[h]);
+      if (lane < 4) wsb[off_sse(g, D) + ((size_t)d * g.nchunk + chunk) * kCh + 2 * lane + h] = s;
+      if (d == 0) {
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+          const double tk = rows_sum(tha[h][k]);
+          if (lane < 4) wsb[off_th(g, D) + ((size_t)chunk * P + k) * kCh + 2 * lane + h] = tk;
+        }
+      }
+    }
+  }
+}
+
+// ---- final: per chain sums of the partials -> lp, d/d sigma_pre, d/d theta_pre --------------------------------------
+__global__ void wide_final(Args a, int D, int P) {
+  const Geo& g = a.g;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int bg = t / kCh, ch = t % kCh;
+  if (bg >= a.pb.B * g.G) return;
+  const int b = bg / g.G, r = (bg % g.G) * kCh + ch;
+  if (r >= a.pb.R) return;
+  const double* wsb = a.ws + (size_t)bg * g.per_bg;
+  const double bt = a.beta_temp[(size_t)b * a.pb.R + r], inv_beta = 1.0 / a.pb.beta[b];
+  double t12 = 0.0;
+  for (int e = 0; e < D * g.nchunk; ++e) t12 += wsb[off_t1(g, D) + (size_t)e * kCh + ch];
+  double t2 = 0.0;
+  for (int e = 0; e < D * g.nchunk; ++e) t2 += wsb[off_t2(g, D) + (size_t)e * kCh + ch];
+  t12 += t2;
+  double t34 = 0.0, logJ = 0.0;
+  for (int d = 0; d < D; ++d) {
+    double sse = 0.0;
+    for (int c = 0; c < g.nchunk; ++c) sse += wsb[off_sse(g, D) + ((size_t)d * g.nchunk + c) * kCh + ch];
+    const double s = a.sig_pre[((size_t)b * a.pb.R + r) * D + d];
+    const double sig2 = magi_softplus(s) + a.pb.LB[b * D + d], Nd = a.pb.N_ds[b * D + d];
+    t34 += Nd * log(2.0 * M_PI * sig2) + sse / sig2;
+    logJ += s - magi_softplus(s);
+    const double sg = magi_sigmoid(s);
+    a.gsig[((size_t)b * a.pb.R + r) * D + d] = bt * (-0.5 * (Nd / sig2 - sse / (sig2 * sig2)) * sg + (1.0 - sg));
+  }
+  for (int k = 0; k < P; ++k) {
+    double v = 0.0;
+    for (int c = 0; c < g.nchunk; ++c) v += wsb[off_th(g, D) + ((size_t)c * P + k) * kCh + ch];
+    const double tau = a.th_pre[((size_t)b * a.pb.R + r) * P + k];
+    const double sg = magi_sigmoid(tau);
+    logJ += tau - magi_softplus(tau);
+    a.gth[((size_t)b * a.pb.R + r) * P + k] = bt * (-0.5 * inv_beta * v * sg + (1.0 - sg));
+  }
+  a.lp[(size_t)b * a.pb.R + r] = bt * (-0.5 * (t12 * inv_beta + t34) + logJ);
+}
+
+int sm_count() {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+template <class M>
+int launch_wide(const Args& a, cudaStream_t st) {
+  const Geo& g = a.g;
+  const dim3 grid(g.nchunk, M::D, a.pb.B * g.G);
+  if (grid.z > 65535) return MAGI_ERR_UNSUPPORTED;
+  const size_t smem = ((size_t)g.np * kCh + kW * 4 * 32 + kCh * M::P) * sizeof(double);
+  if (smem > 200 * 1024) return MAGI_ERR_UNSUPPORTED;
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(wide_pass1<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
+  if ((e = cudaFuncSetAttribute(wide_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
+  if ((e = cudaFuncSetAttribute(wide_pass3<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
+  wide_pass1<M><<<grid, kT, smem, st>>>(a);
+  wide_pass2<<<grid, kT, smem, st>>>(a, M::D);
+  wide_pass3<M><<<grid, kT, smem, st>>>(a);
+  const int nt = a.pb.B * g.G * kCh;
+  wide_final<<<(nt + 127) / 128, 128, 0, st>>>(a, M::D, M::P);
+  return magi_cuda_status(cudaGetLastError());
+}
+
+int model_dims(int id, int& D, int& P) {
+  switch (id) {
+    case MAGI_MODEL_SEIR3: D = Seir3::D; P = Seir3::P; return 0;
+    case MAGI_MODEL_SEIR4: D = Seir4::D; P = Seir4::P; return 0;
+    case MAGI_MODEL_SIRW: D = Sirw::D; P = Sirw::P; return 0;
+    case MAGI_MODEL_LORENZ96: D = Lorenz96::D; P = Lorenz96::P; return 0;
+    default: return -1;
+  }
+}
+
+}  // namespace
+
+extern "C" size_t magi_b200_logpost_grad_wide_workspace_bytes(const magi_problem_t* pb) {
+  if (!pb || pb->B <= 0 || pb->R <= 0 || pb->n <= 1 || pb->D <= 0) return 0;
+  const Geo g = make_geo(pb, sm_count());
+  return g.per_bg * (size_t)pb->B * g.G * sizeof(double);
+}
+
+extern "C" int magi_b200_logpost_grad_wide(const magi_problem_t* pb, const double* X, const double* sig_pre,
+                                           const double* th_pre, const double* beta_temp, double* lp, double* gX,
+                                           double* gsig, double* gth, void* ws, size_t ws_bytes,
+                                           magi_stream_t stream) {
+  if (!pb) return -1;
+  int D, P;
+  if (model_dims(pb->model_id, D, P) != 0) return MAGI_ERR_UNSUPPORTED;
+  if (pb->D != D || pb->P != P || pb->B <= 0 || pb->R <= 0 || pb->n <= 1) return -1;
+  if (!pb->packed || !pb->mu || !pb->y || !pb->mask || !pb->N_ds || !pb->beta || !pb->LB) return -1;
+  if (!X) return -2;
+  if (!sig_pre) return -3;
+  if (!th_pre) return -4;
+  if (!beta_temp) return -5;
+  if (!lp) return -6;
+  if (!gX) return -7;
+  if (!gsig) return -8;
+  if (!gth) return -9;
+  Args a;
+  a.pb = *pb;
+  a.g = make_geo(pb, sm_count());
+  if (!ws || ws_bytes < a.g.per_bg * (size_t)pb->B * a.g.G * sizeof(double)) return -10;
+  a.X = X; a.sig_pre = sig_pre; a.th_pre = th_pre; a.beta_temp = beta_temp;
+  a.lp = lp; a.gX = gX; a.gsig = gsig; a.gth = gth; a.ws = static_cast<double*>(ws);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (pb->model_id) {
+    case MAGI_MODEL_SEIR3: return launch_wide<Seir3>(a, st);
+    case MAGI_MODEL_SEIR4: return launch_wide<Seir4>(a, st);
+    case MAGI_MODEL_SIRW: return launch_wide<Sirw>(a, st);
+    case MAGI_MODEL_LORENZ96: return launch_wide<Lorenz96>(a, st);
+    default: return MAGI_ERR_UNSUPPORTED;
+  }
+}

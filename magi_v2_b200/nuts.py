@@ -418,13 +418,13 @@ class FusedLeafEngine:
         building, log_u_leaf, n_sub = sub["building"], sub["log_u_leaf"], sub["n_sub"]
         ptr = lambda t: Ct.c_void_p(t.data_ptr())
         lp, gX, gs, gt = self.out
-        ws, nb = self.prob.workspace(self.R)
+        evalf, ws, nb = self.prob.eval_call(self.R)            # few datasets: the wide path (magi_b200_wide.h)
         pb = self.prob.struct(self.R)
         st_ref, pb_ref = Ct.byref(st), Ct.byref(pb)
         p_ph, p_Xn, p_sn, p_tn, p_bt = ptr(self.ph), ptr(self.Xn), ptr(self.sn), ptr(self.tn), ptr(self.bt)
         p_lp, p_gX, p_gs, p_gt, p_ws = ptr(lp), ptr(gX), ptr(gs), ptr(gt), (ptr(ws) if ws is not None else None)
         lu0, med, sync_every = log_u_leaf.data_ptr(), float(sub["max_energy_diff"]), sub["sync_every"]
-        pre, evalf, post = lib.magi_b200_nuts_leaf_pre, lib.magi_b200_logpost_grad, lib.magi_b200_nuts_leaf_post
+        pre, post = lib.magi_b200_nuts_leaf_pre, lib.magi_b200_nuts_leaf_post
         no_slots = (Ct.c_int * 1)(0)
         with torch.cuda.device(self.prob.device):
             stream = self._stream()

@@ -170,7 +170,32 @@ class PosteriorProblem:
         mk = lambda *sh: torch.empty(sh, dtype=torch.float64, device=self.device)
         return mk(self.B, R), mk(self.B, R, self.n, self.D), mk(self.B, R, self.D), mk(self.B, R, self.P)
 
-    def logpost_grad(self, X: Tensor, sig_pre: Tensor, th_pre: Tensor, beta_temp: Tensor, out=None):
+    WIDE_MAX_CTAS = 64      # (datasets x chain groups of 8) up to which the rows are spread over the grid instead
+
+    def eval_path(self, R: int, path: str = "auto") -> str:
+        """"cta": magi_b200_logpost_grad, one CTA per (dataset, 8 chains) -- for many datasets; "wide":
+        magi_b200_logpost_grad_wide (include/magi_b200_wide.h), every component's matrix rows spread over the grid
+        -- for few.  Both compute the same function; "auto" picks by how many CTAs the first one would have."""
+        if path == "auto":
+            return "wide" if self.B * ((R + 7) // 8) <= self.WIDE_MAX_CTAS else "cta"
+        if path not in ("cta", "wide"):
+            raise ValueError("path must be 'auto', 'cta' or 'wide'")
+        return path
+
+    def eval_call(self, R: int, path: str = "auto"):
+        """(C entry point, workspace tensor or None, workspace bytes) of the evaluation path for R chains."""
+        if self.eval_path(R, path) == "cta":
+            ws, nb = self.workspace(R)
+            return lib().magi_b200_logpost_grad, ws, nb
+        pb = self.struct(R)
+        nb = lib().magi_b200_logpost_grad_wide_workspace_bytes(C.byref(pb))
+        ws = self._ws.get("wide")
+        if ws is None or ws.numel() * 8 < nb:
+            ws = torch.empty(max(nb // 8, 1), dtype=torch.float64, device=self.device)
+            self._ws["wide"] = ws
+        return lib().magi_b200_logpost_grad_wide, ws, nb
+
+    def logpost_grad(self, X: Tensor, sig_pre: Tensor, th_pre: Tensor, beta_temp: Tensor, out=None, path: str = "auto"):
         """X [B,R,n,D], sig_pre [B,R,D], th_pre [B,R,P], beta_temp [B,R] ->
         (lp [B,R], gX, gsig, gth) -- value and gradient of magi_v2.py:308-348."""
         R = X.shape[1]
@@ -181,10 +206,10 @@ class PosteriorProblem:
             if out is not None:
                 _chk(lp, "lp", shape=(self.B, R)); _chk(gX, "gX", shape=X.shape)
                 _chk(gsig, "gsig", shape=sig_pre.shape); _chk(gth, "gth", shape=th_pre.shape)
-            ws, nb = self.workspace(R)
+            fn, ws, nb = self.eval_call(R, path)
             pb = self.struct(R)
-            st = lib().magi_b200_logpost_grad(C.byref(pb), _ptr(X), _ptr(sig_pre), _ptr(th_pre), _ptr(beta_temp),
-                                              _ptr(lp), _ptr(gX), _ptr(gsig), _ptr(gth), _ptr(ws), nb, _stream(X))
+            st = fn(C.byref(pb), _ptr(X), _ptr(sig_pre), _ptr(th_pre), _ptr(beta_temp),
+                    _ptr(lp), _ptr(gX), _ptr(gsig), _ptr(gth), _ptr(ws), nb, _stream(X))
         check(st, "logpost_grad")
         return lp, gX, gsig, gth
 

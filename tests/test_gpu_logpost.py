@@ -11,17 +11,21 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-9
 
 
-def _run(prob, X, s, tau, bt, device):
+PATHS = ["cta", "wide"]      # magi_b200_logpost_grad / magi_b200_logpost_grad_wide: same function, two grid shapes
+
+
+def _run(prob, X, s, tau, bt, device, path="cta"):
     import torch
     T = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=device)
-    lp, gX, gs, gt = prob.logpost_grad(T(X), T(s), T(tau), T(bt))
+    lp, gX, gs, gt = prob.logpost_grad(T(X), T(s), T(tau), T(bt), path=path)
     torch.cuda.synchronize()
     return lp.cpu().numpy(), gX.cpu().numpy(), gs.cpu().numpy(), gt.cpu().numpy()
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("model", ["seir3", "seir4", "sirw", "lorenz96"])
 @pytest.mark.parametrize("R", [1, 8, 11])
-def test_small_batches_match_oracle(model, R, cuda_device):
+def test_small_batches_match_oracle(model, R, path, cuda_device):
     B = 3
     rng = np.random.default_rng(10 + R)
     consts = [synth_constants(model, seed=100 + b) for b in range(B)]
@@ -29,7 +33,7 @@ def test_small_batches_match_oracle(model, R, cuda_device):
     st = [random_state(c, model, rng, R) for c in consts]
     X = np.stack([a[0] for a in st]); s = np.stack([a[1] for a in st]); tau = np.stack([a[2] for a in st])
     bt = rng.uniform(0.1, 1.5, (B, R))
-    lp, gX, gs, gt = _run(prob, X, s, tau, bt, cuda_device)
+    lp, gX, gs, gt = _run(prob, X, s, tau, bt, cuda_device, path)
     for b in range(B):
         for r in range(R):
             o = mo.log_posterior_and_grad_autograd(X[b, r], s[b, r], tau[b, r], bt[b, r], consts[b])
@@ -39,8 +43,9 @@ def test_small_batches_match_oracle(model, R, cuda_device):
             assert relerr(gt[b, r], o[3]) <= TOL
 
 
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("model", ["seir3", "seir4"])
-def test_seir_vignette_shape(model, cuda_device):
+def test_seir_vignette_shape(model, path, cuda_device):
     """n = 161, band 80: the reference's own configuration (vignette.ipynb:163)."""
     rng = np.random.default_rng(5)
     c, _, _ = seir_vignette_constants(0, model)
@@ -48,7 +53,7 @@ def test_seir_vignette_shape(model, cuda_device):
     X, s, tau = random_state(c, model, rng, 8, jitter=0.01)
     tau[:, :3] = np.array([6.0, 0.1, 1.6]) + 0.1 * rng.standard_normal((8, 3))
     bt = np.full((1, 8), 0.37)
-    lp, gX, gs, gt = _run(prob, X[None], s[None], tau[None], bt, cuda_device)
+    lp, gX, gs, gt = _run(prob, X[None], s[None], tau[None], bt, cuda_device, path)
     for r in (0, 3, 7):
         o = mo.log_posterior_and_grad_autograd(X[r], s[r], tau[r], 0.37, c)
         assert abs(lp[0, r] - o[0]) <= TOL * abs(o[0])
@@ -57,7 +62,8 @@ def test_seir_vignette_shape(model, cuda_device):
         assert relerr(gt[0, r], o[3]) <= TOL
 
 
-def test_committed_golden_vectors(cuda_device):
+@pytest.mark.parametrize("path", PATHS)
+def test_committed_golden_vectors(path, cuda_device):
     """Inputs and expected outputs fixed in tests/golden/logpost_kat.npz (matrices from the genuine
     reference `_build_matrices`)."""
     import torch
@@ -70,32 +76,35 @@ def test_committed_golden_vectors(cuda_device):
                               model.f_vec, matrices=mats)
         prob = device_problem([c], name, cuda_device)
         lp, gX, gs, gt = _run(prob, g[f"{name}_X"][None, None], g[f"{name}_s"][None, None],
-                              g[f"{name}_tau"][None, None], np.full((1, 1), float(g[f"{name}_bt"])), cuda_device)
+                              g[f"{name}_tau"][None, None], np.full((1, 1), float(g[f"{name}_bt"])), cuda_device,
+                              path)
         assert abs(lp[0, 0] - g[f"{name}_lp"]) <= TOL * abs(g[f"{name}_lp"])
         assert relerr(gX[0, 0], g[f"{name}_gX"]) <= TOL
         assert relerr(gs[0, 0], g[f"{name}_gs"]) <= TOL
         assert relerr(gt[0, 0], g[f"{name}_gt"]) <= TOL
 
 
-def test_linearity_in_temperature_and_chain_independence(cuda_device):
+@pytest.mark.parametrize("path", PATHS)
+def test_linearity_in_temperature_and_chain_independence(path, cuda_device):
     """Size-independent properties: lp and gradient scale linearly with beta_temp (:348), and a chain's
     result does not depend on which other chains share its CTA."""
     rng = np.random.default_rng(7)
     c = synth_constants("seir4", seed=3, N=21, band=None)
     prob = device_problem([c], "seir4", cuda_device)
     X, s, tau = random_state(c, "seir4", rng, 8)
-    a = _run(prob, X[None], s[None], tau[None], np.full((1, 8), 1.0), cuda_device)
-    b = _run(prob, X[None], s[None], tau[None], np.full((1, 8), 0.25), cuda_device)
+    a = _run(prob, X[None], s[None], tau[None], np.full((1, 8), 1.0), cuda_device, path)
+    b = _run(prob, X[None], s[None], tau[None], np.full((1, 8), 0.25), cuda_device, path)
     for u, v in zip(a, b):
         assert relerr(0.25 * u, v) <= 1e-14
     perm = rng.permutation(8)
-    p = _run(prob, X[None, perm], s[None, perm], tau[None, perm], np.full((1, 8), 1.0), cuda_device)
+    p = _run(prob, X[None, perm], s[None, perm], tau[None, perm], np.full((1, 8), 1.0), cuda_device, path)
     for u, v in zip(a, p):
         assert np.array_equal(u[0][perm], v[0])
 
 
 @pytest.mark.parametrize("model", ["seir4", "lorenz96"])
-def test_band_skipping_equals_dense(model, cuda_device):
+@pytest.mark.parametrize("path", PATHS)
+def test_band_skipping_equals_dense(model, path, cuda_device):
     """Telling the kernels the bandsize (zero tiles are then not read) must not change the result:
     same banded matrices evaluated as banded and as dense (fast path and general path)."""
     rng = np.random.default_rng(21)
@@ -106,14 +115,15 @@ def test_band_skipping_equals_dense(model, cuda_device):
     for band in ("auto", None):
         prob = device_problem([c], model, cuda_device, band=band)
         assert prob.band == (12 if band == "auto" else -1)
-        res.append(_run(prob, X[None], s[None], tau[None], bt, cuda_device))
+        res.append(_run(prob, X[None], s[None], tau[None], bt, cuda_device, path))
     for u, v in zip(*res):
         assert relerr(u, v) <= 1e-13
     o = mo.log_posterior_and_grad_autograd(X[3], s[3], tau[3], 0.8, c)
     assert abs(res[0][0][0, 3] - o[0]) <= TOL * abs(o[0]) and relerr(res[0][1][0, 3], o[1]) <= TOL
 
 
-def test_sirw_n321_general_path(cuda_device):
+@pytest.mark.parametrize("path", PATHS)
+def test_sirw_n321_general_path(path, cuda_device):
     """Config 3 (SIRW, n = 321, D = 4, P = 5): np > 168, so the general path (vector arrays in the caller's
     workspace) runs.  Matrices from the oracle's reference route; parity to 1e-9."""
     rng = np.random.default_rng(33)
@@ -122,14 +132,15 @@ def test_sirw_n321_general_path(cuda_device):
     prob = device_problem([c], "sirw", cuda_device)
     X, s, tau = random_state(c, "sirw", rng, 8, jitter=0.01)
     bt = np.full((1, 8), 0.5)
-    lp, gX, gs, gt = _run(prob, X[None], s[None], tau[None], bt, cuda_device)
+    lp, gX, gs, gt = _run(prob, X[None], s[None], tau[None], bt, cuda_device, path)
     for r in (0, 5):
         o = mo.log_posterior_and_grad_autograd(X[r], s[r], tau[r], 0.5, c)
         assert abs(lp[0, r] - o[0]) <= TOL * abs(o[0])
         assert relerr(gX[0, r], o[1]) <= TOL and relerr(gs[0, r], o[2]) <= TOL and relerr(gt[0, r], o[3]) <= TOL
 
 
-def test_lorenz96_large_grid_properties(cuda_device):
+@pytest.mark.parametrize("path", PATHS)
+def test_lorenz96_large_grid_properties(path, cuda_device):
     """Config 5 shape (Lorenz-96, D = 10) at n = 641 with device-built matrices: too large for the oracle to
     finish in seconds, so the size-independent properties are checked -- linearity in beta_temp, independence
     of a chain from its CTA neighbours, and agreement of banded-as-banded with banded-as-dense."""
@@ -152,17 +163,17 @@ def test_lorenz96_large_grid_properties(cuda_device):
     res = {}
     for band in (160, None):
         prob = ops.PosteriorProblem("lorenz96", packed, band=band, **consts)
-        res[band] = [a.cpu().numpy() for a in prob.logpost_grad(T(X), T(s), T(tau), T(np.full((1, R), 1.0)))]
+        res[band] = [a.cpu().numpy() for a in prob.logpost_grad(T(X), T(s), T(tau), T(np.full((1, R), 1.0)), path=path)]
         assert all(np.isfinite(a).all() for a in res[band])
     for u, v in zip(res[160], res[None]):
         assert relerr(u, v) <= 1e-12
     prob = ops.PosteriorProblem("lorenz96", packed, band=160, **consts)
-    q = [a.cpu().numpy() for a in prob.logpost_grad(T(X), T(s), T(tau), T(np.full((1, R), 0.25)))]
+    q = [a.cpu().numpy() for a in prob.logpost_grad(T(X), T(s), T(tau), T(np.full((1, R), 0.25)), path=path)]
     for u, v in zip(res[160], q):
         assert relerr(0.25 * u, v) <= 1e-14
     perm = rng.permutation(R)
     p = [a.cpu().numpy() for a in prob.logpost_grad(T(X[:, perm]), T(s[:, perm]), T(tau[:, perm]),
-                                                    T(np.full((1, R), 1.0)))]
+                                                    T(np.full((1, R), 1.0)), path=path)]
     for u, v in zip(res[160], p):   # (general path: chains 0-4 are summed by 3 warps, 5-7 by 2 -> not bit-identical)
         assert relerr(u[0][perm], v[0]) <= 1e-13
     # and against an independent float64 numpy evaluation of the same formula with the device-built matrices
