@@ -30,9 +30,9 @@ struct Geo {
 __host__ __device__ inline size_t off_R(const Geo&, int) { return 0; }
 __host__ __device__ inline size_t off_Q(const Geo& g, int D) { return (size_t)D * g.np * kCh; }
 __host__ __device__ inline size_t off_t1(const Geo& g, int D) { return 2 * (size_t)D * g.np * kCh; }
-__host__ __device__ inline size_t off_t2(const Geo& g, int D) { return off_t1(g, D) + (size_t)D * g.nchunk * kCh; }
-__host__ __device__ inline size_t off_sse(const Geo& g, int D) { return off_t2(g, D) + (size_t)D * g.nchunk * kCh; }
-__host__ __device__ inline size_t off_th(const Geo& g, int D) { return off_sse(g, D) + (size_t)D * g.nchunk * kCh; }
+__host__ __device__ inline size_t off_t2(const Geo& g, int D) { return off_t1(g, D) + (size_t)D * g.nblk * kCh; }
+__host__ __device__ inline size_t off_sse(const Geo& g, int D) { return off_t2(g, D) + (size_t)D * g.nblk * kCh; }
+__host__ __device__ inline size_t off_th(const Geo& g, int D) { return off_sse(g, D) + (size_t)D * g.nblk * kCh; }
 
 Geo make_geo(const magi_problem_t* pb, int sms) {
   Geo g;
@@ -44,7 +44,7 @@ Geo make_geo(const magi_problem_t* pb, int sms) {
   long r = ctas1 / (4L * sms);
   g.rbpc = (int)(r < 1 ? 1 : (r > 8 ? 8 : r));
   g.nchunk = (g.nblk + g.rbpc - 1) / g.rbpc;
-  g.per_bg = off_th(g, pb->D) + (size_t)g.nchunk * pb->P * kCh;
+  g.per_bg = off_th(g, pb->D) + (size_t)g.nblk * pb->P * kCh;
   return g;
 }
 
@@ -98,8 +98,16 @@ struct Args {
   double* ws;
 };
 
+// Two work splits, same arithmetic.  ROWW = false (few block rows per CTA: small n / very few datasets): the CTA's 8
+// warps split the tile columns of one block row and their partial products are summed through shared memory.
+// ROWW = true (8 block rows per CTA: enough rows to fill the grid): each warp owns a block row and streams all of its
+// tiles -- no barrier and no reduction inside the loop.
+#define MAGI_WIDE_ROWS(I)                                                   \
+  const int I0 = chunk * g.rbpc, I1 = min(g.nblk, I0 + g.rbpc);             \
+  for (int I = ROWW ? I0 + warp : I0; I < I1; I += ROWW ? kW : 1)
+
 // ---- pass 1: u = S_C x_c, v = m x_c, r = f - v, t1 ------------------------------------------------------------
-template <class M>
+template <class M, bool ROWW>
 __global__ void __launch_bounds__(kT) wide_pass1(Args a) {
   extern __shared__ double sm[];
   constexpr int D = M::D, P = M::P;
@@ -122,15 +130,13 @@ __global__ void __launch_bounds__(kT) wide_pass1(Args a) {
   const double* matM = matC + (size_t)g.np * g.np;
   double* wsb = a.ws + (size_t)bg * g.per_bg;
   double* Rr = wsb + off_R(g, D);
-  double t1acc[2] = {0.0, 0.0};
   __syncthreads();
-  const int I1 = min(g.nblk, (chunk + 1) * g.rbpc);
-  for (int I = chunk * g.rbpc; I < I1; ++I) {
+  MAGI_WIDE_ROWS(I) {
     int lo, hi;
     jrange(g, I, lo, hi);
     double c[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 2
-    for (int J = lo + warp; J <= hi; J += kW) {
+    for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : kW) {
       const size_t t = ((size_t)I * g.nblk + J) * 64 + (lane >> 2) * 8 + (lane & 3);
       const double a0 = matC[t], a1 = matC[t + 4], m0 = matM[t], m1 = matM[t + 4];
       const double b0 = vs[(J * 8 + (lane & 3)) * 8 + (lane >> 2)], b1 = vs[(J * 8 + 4 + (lane & 3)) * 8 + (lane >> 2)];
@@ -139,13 +145,13 @@ __global__ void __launch_bounds__(kT) wide_pass1(Args a) {
       dmma(c[2], c[3], m0, b0);
       dmma(c[2], c[3], m1, b1);
     }
-    cta_reduce<4>(c, red);
-    if (warp == 0) {
+    if (!ROWW) cta_reduce<4>(c, red);
+    if (ROWW || warp == 0) {
       const int i = I * 8 + (lane >> 2);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int ch = 2 * (lane & 3) + h, r = grp * kCh + ch;
-        double rv = 0.0;
+        double rv = 0.0, t1 = 0.0;
         if (i < n && r < R) {
           const double* xp = a.X + (((size_t)b * R + r) * n + i) * D;
           double x[D], fo[D];
@@ -157,22 +163,18 @@ __global__ void __launch_bounds__(kT) wide_pass1(Args a) {
           for (int dd = 0; dd < D; ++dd) fd = dd == d ? fo[dd] : fd;
           rv = fd - c[2 + h];
           a.gX[(((size_t)b * R + r) * n + i) * D + d] = 2.0 * c[h];   // scratch: 2 u, finished in pass 3
-          t1acc[h] = fma(vs[i * 8 + ch], c[h], t1acc[h]);
+          t1 = vs[i * 8 + ch] * c[h];
         }
         Rr[((size_t)d * g.np + i) * kCh + ch] = rv;
+        t1 = rows_sum(t1);
+        if (lane < 4) wsb[off_t1(g, D) + ((size_t)d * g.nblk + I) * kCh + ch] = t1;
       }
-    }
-  }
-  if (warp == 0) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const double s = rows_sum(t1acc[h]);
-      if (lane < 4) wsb[off_t1(g, D) + ((size_t)d * g.nchunk + chunk) * kCh + 2 * lane + h] = s;
     }
   }
 }
 
 // ---- pass 2: q = S_K r, t2 ---------------------------------------------------------------------------------------
+template <bool ROWW>
 __global__ void __launch_bounds__(kT) wide_pass2(Args a, int D) {
   extern __shared__ double sm[];
   const Geo& g = a.g;
@@ -185,42 +187,34 @@ __global__ void __launch_bounds__(kT) wide_pass2(Args a, int D) {
   double* Q = wsb + off_Q(g, D) + (size_t)d * g.np * kCh;
   for (int e = tid; e < g.np * kCh; e += kT) vs[e] = Rr[e];
   const double* matK = static_cast<const double*>(a.pb.packed) + ((size_t)(b * D + d) * 3 + 2) * g.np * g.np;
-  double t2acc[2] = {0.0, 0.0};
   __syncthreads();
-  const int I1 = min(g.nblk, (chunk + 1) * g.rbpc);
-  for (int I = chunk * g.rbpc; I < I1; ++I) {
+  MAGI_WIDE_ROWS(I) {
     int lo, hi;
     jrange(g, I, lo, hi);
     double c[2] = {0.0, 0.0};
 #pragma unroll 4
-    for (int J = lo + warp; J <= hi; J += kW) {
+    for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : kW) {
       const size_t t = ((size_t)I * g.nblk + J) * 64 + (lane >> 2) * 8 + (lane & 3);
       const double a0 = matK[t], a1 = matK[t + 4];
       dmma(c[0], c[1], a0, vs[(J * 8 + (lane & 3)) * 8 + (lane >> 2)]);
       dmma(c[0], c[1], a1, vs[(J * 8 + 4 + (lane & 3)) * 8 + (lane >> 2)]);
     }
-    cta_reduce<2>(c, red);
-    if (warp == 0) {
+    if (!ROWW) cta_reduce<2>(c, red);
+    if (ROWW || warp == 0) {
       const int i = I * 8 + (lane >> 2);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int ch = 2 * (lane & 3) + h;
         Q[(size_t)i * kCh + ch] = c[h];      // rows >= n: zero tiles times zero r -> 0
-        t2acc[h] = fma(vs[i * 8 + ch], c[h], t2acc[h]);
+        const double t2 = rows_sum(vs[i * 8 + ch] * c[h]);
+        if (lane < 4) wsb[off_t2(g, D) + ((size_t)d * g.nblk + I) * kCh + ch] = t2;
       }
-    }
-  }
-  if (warp == 0) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const double s = rows_sum(t2acc[h]);
-      if (lane < 4) wsb[off_t2(g, D) + ((size_t)d * g.nchunk + chunk) * kCh + 2 * lane + h] = s;
     }
   }
 }
 
 // ---- pass 3: m^T q and the point-wise assembly of dX; SSE and d/d theta partial sums -------------------------------
-template <class M>
+template <class M, bool ROWW>
 __global__ void __launch_bounds__(kT) wide_pass3(Args a) {
   extern __shared__ double sm[];
   constexpr int D = M::D, P = M::P;
@@ -239,11 +233,6 @@ __global__ void __launch_bounds__(kT) wide_pass3(Args a) {
   }
   const double* matM = static_cast<const double*>(a.pb.packed) + ((size_t)(b * D + d) * 3 + 1) * g.np * g.np;
   const double inv_beta = 1.0 / a.pb.beta[b];
-  double sse[2] = {0.0, 0.0}, tha[2][P];
-#pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int k = 0; k < P; ++k) tha[h][k] = 0.0;
   double bt[2], isig2[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -252,28 +241,30 @@ __global__ void __launch_bounds__(kT) wide_pass3(Args a) {
     isig2[h] = r < R ? 1.0 / (magi_softplus(a.sig_pre[((size_t)b * R + r) * D + d]) + a.pb.LB[b * D + d]) : 0.0;
   }
   __syncthreads();
-  const int I1 = min(g.nblk, (chunk + 1) * g.rbpc);
-  for (int I = chunk * g.rbpc; I < I1; ++I) {
+  MAGI_WIDE_ROWS(I) {
     int lo, hi;
     jrange(g, I, lo, hi);
     double c[2] = {0.0, 0.0};
 #pragma unroll 4
-    for (int J = lo + warp; J <= hi; J += kW) {
+    for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : kW) {
       // (m^T)(I, J) = tile (J, I) transposed: A[row][k] = tile[k][row]
       const size_t t = ((size_t)J * g.nblk + I) * 64 + (lane & 3) * 8 + (lane >> 2);
       const double a0 = matM[t], a1 = matM[t + 32];
       dmma(c[0], c[1], a0, vs[(J * 8 + (lane & 3)) * 8 + (lane >> 2)]);
       dmma(c[0], c[1], a1, vs[(J * 8 + 4 + (lane & 3)) * 8 + (lane >> 2)]);
     }
-    cta_reduce<2>(c, red);
-    if (warp == 0) {
+    if (!ROWW) cta_reduce<2>(c, red);
+    if (ROWW || warp == 0) {
       const int i = I * 8 + (lane >> 2);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int ch = 2 * (lane & 3) + h, r = grp * kCh + ch;
+        double sse = 0.0, vth[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) vth[k] = 0.0;
         if (i < n && r < R) {
           const size_t xo = (((size_t)b * R + r) * n + i) * D;
-          double x[D], gq[D], vx[D], vth[P];
+          double x[D], gq[D], vx[D];
 #pragma unroll
           for (int dd = 0; dd < D; ++dd) {
             x[dd] = a.X[xo + dd];
@@ -290,25 +281,16 @@ __global__ void __launch_bounds__(kT) wide_pass3(Args a) {
           const size_t yo = ((size_t)b * n + i) * D + d;
           const double e = a.pb.mask[yo] ? xd - a.pb.y[yo] : 0.0;
           a.gX[xo + d] = bt[h] * -0.5 * (prior * inv_beta + 2.0 * e * isig2[h]);
-          sse[h] = fma(e, e, sse[h]);
-          if (d == 0) {
-#pragma unroll
-            for (int k = 0; k < P; ++k) tha[h][k] += vth[k];
-          }
+          sse = e * e;
         }
-      }
-    }
-  }
-  if (warp == 0) {
+        sse = rows_sum(sse);
+        if (lane < 4) wsb[off_sse(g, D) + ((size_t)d * g.nblk + I) * kCh + ch] = sse;
+        if (d == 0) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const double s = rows_sum(sse[h]);
-      if (lane < 4) wsb[off_sse(g, D) + ((size_t)d * g.nchunk + chunk) * kCh + 2 * lane + h] = s;
-      if (d == 0) {
-#pragma unroll
-        for (int k = 0; k < P; ++k) {
-          const double tk = rows_sum(tha[h][k]);
-          if (lane < 4) wsb[off_th(g, D) + ((size_t)chunk * P + k) * kCh + 2 * lane + h] = tk;
+          for (int k = 0; k < P; ++k) {
+            const double tk = rows_sum(vth[k]);
+            if (lane < 4) wsb[off_th(g, D) + ((size_t)I * P + k) * kCh + ch] = tk;
+          }
         }
       }
     }
@@ -326,14 +308,14 @@ __global__ void wide_final(Args a, int D, int P) {
   const double* wsb = a.ws + (size_t)bg * g.per_bg;
   const double bt = a.beta_temp[(size_t)b * a.pb.R + r], inv_beta = 1.0 / a.pb.beta[b];
   double t12 = 0.0;
-  for (int e = 0; e < D * g.nchunk; ++e) t12 += wsb[off_t1(g, D) + (size_t)e * kCh + ch];
+  for (int e = 0; e < D * g.nblk; ++e) t12 += wsb[off_t1(g, D) + (size_t)e * kCh + ch];
   double t2 = 0.0;
-  for (int e = 0; e < D * g.nchunk; ++e) t2 += wsb[off_t2(g, D) + (size_t)e * kCh + ch];
+  for (int e = 0; e < D * g.nblk; ++e) t2 += wsb[off_t2(g, D) + (size_t)e * kCh + ch];
   t12 += t2;
   double t34 = 0.0, logJ = 0.0;
   for (int d = 0; d < D; ++d) {
     double sse = 0.0;
-    for (int c = 0; c < g.nchunk; ++c) sse += wsb[off_sse(g, D) + ((size_t)d * g.nchunk + c) * kCh + ch];
+    for (int c = 0; c < g.nblk; ++c) sse += wsb[off_sse(g, D) + ((size_t)d * g.nblk + c) * kCh + ch];
     const double s = a.sig_pre[((size_t)b * a.pb.R + r) * D + d];
     const double sig2 = magi_softplus(s) + a.pb.LB[b * D + d], Nd = a.pb.N_ds[b * D + d];
     t34 += Nd * log(2.0 * M_PI * sig2) + sse / sig2;
@@ -343,7 +325,7 @@ __global__ void wide_final(Args a, int D, int P) {
   }
   for (int k = 0; k < P; ++k) {
     double v = 0.0;
-    for (int c = 0; c < g.nchunk; ++c) v += wsb[off_th(g, D) + ((size_t)c * P + k) * kCh + ch];
+    for (int c = 0; c < g.nblk; ++c) v += wsb[off_th(g, D) + ((size_t)c * P + k) * kCh + ch];
     const double tau = a.th_pre[((size_t)b * a.pb.R + r) * P + k];
     const double sg = magi_sigmoid(tau);
     logJ += tau - magi_softplus(tau);
@@ -358,23 +340,28 @@ int sm_count() {
   return sms;
 }
 
-template <class M>
-int launch_wide(const Args& a, cudaStream_t st) {
+template <class M, bool ROWW>
+int launch_wide_t(const Args& a, cudaStream_t st) {
   const Geo& g = a.g;
   const dim3 grid(g.nchunk, M::D, a.pb.B * g.G);
   if (grid.z > 65535) return MAGI_ERR_UNSUPPORTED;
   const size_t smem = ((size_t)g.np * kCh + kW * 4 * 32 + kCh * M::P) * sizeof(double);
   if (smem > 200 * 1024) return MAGI_ERR_UNSUPPORTED;
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(wide_pass1<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
-  if ((e = cudaFuncSetAttribute(wide_pass2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
-  if ((e = cudaFuncSetAttribute(wide_pass3<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
-  wide_pass1<M><<<grid, kT, smem, st>>>(a);
-  wide_pass2<<<grid, kT, smem, st>>>(a, M::D);
-  wide_pass3<M><<<grid, kT, smem, st>>>(a);
+  if ((e = cudaFuncSetAttribute(wide_pass1<M, ROWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
+  if ((e = cudaFuncSetAttribute(wide_pass2<ROWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
+  if ((e = cudaFuncSetAttribute(wide_pass3<M, ROWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
+  wide_pass1<M, ROWW><<<grid, kT, smem, st>>>(a);
+  wide_pass2<ROWW><<<grid, kT, smem, st>>>(a, M::D);
+  wide_pass3<M, ROWW><<<grid, kT, smem, st>>>(a);
   const int nt = a.pb.B * g.G * kCh;
   wide_final<<<(nt + 127) / 128, 128, 0, st>>>(a, M::D, M::P);
   return magi_cuda_status(cudaGetLastError());
+}
+
+template <class M>
+int launch_wide(const Args& a, cudaStream_t st) {
+  return a.g.rbpc == kW ? launch_wide_t<M, true>(a, st) : launch_wide_t<M, false>(a, st);
 }
 
 int model_dims(int id, int& D, int& P) {

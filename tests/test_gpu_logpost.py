@@ -185,3 +185,38 @@ def test_lorenz96_large_grid_properties(path, cuda_device):
                                 beta=float(D * n / (81.0 * D)), sigma_sqs_LB=np.full(D, 1e-4), f_vec=mo2.f_lorenz96)
     o = mo2.log_posterior_and_grad_autograd(X[0, 2], s[0, 2], tau[0, 2], 1.0, oc)
     assert abs(res[160][0][0, 2] - o[0]) <= TOL * abs(o[0]) and relerr(res[160][1][0, 2], o[1]) <= TOL
+
+
+def test_wide_path_row_per_warp_split_matches_cta_path(cuda_device):
+    """With enough block rows to fill the grid (here n = 641, D = 10, 48 chains: 81 * 10 * 6 block-row tasks) the
+    wide path gives each warp a whole block row instead of splitting a row's tiles over the CTA's warps; the two
+    grid shapes of the evaluation must still agree to rounding, and one chain is checked against the oracle."""
+    import torch
+    from magi_v2_b200 import ops
+    rng = np.random.default_rng(19)
+    n, D, R = 641, 10, 48
+    I = np.linspace(0, 4, n)
+    T = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=cuda_device)
+    phi1, phi2 = rng.uniform(0.5, 2.0, (1, D)), rng.uniform(0.15, 0.3, (1, D))
+    C, Cp, Cpp = ops.cov_build(T(I), T(phi1), T(phi2), 2.01, True)
+    Cinv, m, Kinv, _, info = ops.factor_derive(C, Cp, Cpp, 160, 0.0)
+    assert int(info.abs().max()) == 0
+    mask = np.zeros((1, n, D), dtype=np.uint8); mask[:, ::8] = 1
+    y = rng.normal(2.0, 3.0, (1, n, D)) * mask
+    prob = ops.PosteriorProblem("lorenz96", ops.pack_matrices(Cinv, m, Kinv), mu=T(np.full((1, D), 2.0)), y=T(y),
+                                mask=T(mask, torch.uint8), N_ds=T(np.full((1, D), 81.0)),
+                                beta=T(np.array([D * n / (81.0 * D)])), LB=T(np.full((1, D), 1e-4)), n=n, band=160)
+    X = rng.normal(2.0, 3.0, (1, R, n, D)); s = rng.normal(-1, 0.5, (1, R, D)); tau = rng.normal(2.0, 0.2, (1, R, 1))
+    bt = rng.uniform(0.2, 1.2, (1, R))
+    res = {p: [a.cpu().numpy() for a in prob.logpost_grad(T(X), T(s), T(tau), T(bt), path=p)] for p in PATHS}
+    for u, v in zip(res["cta"], res["wide"]):
+        assert np.isfinite(v).all() and relerr(v, u) <= 1e-12
+    idx = np.where(mask[0].reshape(-1) > 0)[0]
+    oc = mo.PosteriorConstants(I=I.reshape(-1, 1), mu_ds=np.full(D, 2.0), C_d_invs=Cinv[0].cpu().numpy(),
+                               m_ds=m[0].cpu().numpy(), K_d_invs=Kinv[0].cpu().numpy(), N_ds=np.full(D, 81.0),
+                               not_nan_idxs=idx, not_nan_cols=idx % D, y_tau_ds_observed=y[0].reshape(-1)[idx],
+                               beta=float(D * n / (81.0 * D)), sigma_sqs_LB=np.full(D, 1e-4), f_vec=mo.f_lorenz96)
+    r = 41
+    o = mo.log_posterior_and_grad_autograd(X[0, r], s[0, r], tau[0, r], bt[0, r], oc)
+    assert abs(res["wide"][0][0, r] - o[0]) <= TOL * abs(o[0]) and relerr(res["wide"][1][0, r], o[1]) <= TOL
+    assert relerr(res["wide"][3][0, r], o[3]) <= TOL and relerr(res["wide"][2][0, r], o[2]) <= TOL
