@@ -8,6 +8,8 @@
 // (mma.sync.m8n8k4: A = half a tile, coalesced 256 B per warp load, also for the transposed pass; B = 4 x 8 slice of
 // the vector array in shared memory, conflict-free), then a cross-warp reduction.  HBM-bound: every matrix byte is
 // read once per pass by exactly one warp.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ode_models.cuh"
 #include "../../include/magi_b200_wide.h"
@@ -298,40 +300,42 @@ __global__ void __launch_bounds__(kT) wide_pass3(Args a) {
 }
 
 // ---- final: per chain sums of the partials -> lp, d/d sigma_pre, d/d theta_pre --------------------------------------
-__global__ void wide_final(Args a, int D, int P) {
+// One CTA per (dataset, chain group), one warp per chain: the lanes stride over the per-block-row partial sums and
+// combine them by shuffles (fixed order: deterministic).
+__global__ void __launch_bounds__(kT) wide_final(Args a, int D, int P) {
   const Geo& g = a.g;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int bg = t / kCh, ch = t % kCh;
-  if (bg >= a.pb.B * g.G) return;
+  const int bg = blockIdx.x, ch = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = bg / g.G, r = (bg % g.G) * kCh + ch;
   if (r >= a.pb.R) return;
   const double* wsb = a.ws + (size_t)bg * g.per_bg;
   const double bt = a.beta_temp[(size_t)b * a.pb.R + r], inv_beta = 1.0 / a.pb.beta[b];
   double t12 = 0.0;
-  for (int e = 0; e < D * g.nblk; ++e) t12 += wsb[off_t1(g, D) + (size_t)e * kCh + ch];
-  double t2 = 0.0;
-  for (int e = 0; e < D * g.nblk; ++e) t2 += wsb[off_t2(g, D) + (size_t)e * kCh + ch];
-  t12 += t2;
+  for (int e = lane; e < D * g.nblk; e += 32)
+    t12 += wsb[off_t1(g, D) + (size_t)e * kCh + ch] + wsb[off_t2(g, D) + (size_t)e * kCh + ch];
+  t12 = magi_warp_sum(t12);
   double t34 = 0.0, logJ = 0.0;
   for (int d = 0; d < D; ++d) {
     double sse = 0.0;
-    for (int c = 0; c < g.nblk; ++c) sse += wsb[off_sse(g, D) + ((size_t)d * g.nblk + c) * kCh + ch];
+    for (int c = lane; c < g.nblk; c += 32) sse += wsb[off_sse(g, D) + ((size_t)d * g.nblk + c) * kCh + ch];
+    sse = magi_warp_sum(sse);
     const double s = a.sig_pre[((size_t)b * a.pb.R + r) * D + d];
     const double sig2 = magi_softplus(s) + a.pb.LB[b * D + d], Nd = a.pb.N_ds[b * D + d];
     t34 += Nd * log(2.0 * M_PI * sig2) + sse / sig2;
     logJ += s - magi_softplus(s);
     const double sg = magi_sigmoid(s);
-    a.gsig[((size_t)b * a.pb.R + r) * D + d] = bt * (-0.5 * (Nd / sig2 - sse / (sig2 * sig2)) * sg + (1.0 - sg));
+    if (lane == 0)
+      a.gsig[((size_t)b * a.pb.R + r) * D + d] = bt * (-0.5 * (Nd / sig2 - sse / (sig2 * sig2)) * sg + (1.0 - sg));
   }
   for (int k = 0; k < P; ++k) {
     double v = 0.0;
-    for (int c = 0; c < g.nblk; ++c) v += wsb[off_th(g, D) + ((size_t)c * P + k) * kCh + ch];
+    for (int c = lane; c < g.nblk; c += 32) v += wsb[off_th(g, D) + ((size_t)c * P + k) * kCh + ch];
+    v = magi_warp_sum(v);
     const double tau = a.th_pre[((size_t)b * a.pb.R + r) * P + k];
     const double sg = magi_sigmoid(tau);
     logJ += tau - magi_softplus(tau);
-    a.gth[((size_t)b * a.pb.R + r) * P + k] = bt * (-0.5 * inv_beta * v * sg + (1.0 - sg));
+    if (lane == 0) a.gth[((size_t)b * a.pb.R + r) * P + k] = bt * (-0.5 * inv_beta * v * sg + (1.0 - sg));
   }
-  a.lp[(size_t)b * a.pb.R + r] = bt * (-0.5 * (t12 * inv_beta + t34) + logJ);
+  if (lane == 0) a.lp[(size_t)b * a.pb.R + r] = bt * (-0.5 * (t12 * inv_beta + t34) + logJ);
 }
 
 int sm_count() {
@@ -354,14 +358,15 @@ int launch_wide_t(const Args& a, cudaStream_t st) {
   wide_pass1<M, ROWW><<<grid, kT, smem, st>>>(a);
   wide_pass2<ROWW><<<grid, kT, smem, st>>>(a, M::D);
   wide_pass3<M, ROWW><<<grid, kT, smem, st>>>(a);
-  const int nt = a.pb.B * g.G * kCh;
-  wide_final<<<(nt + 127) / 128, 128, 0, st>>>(a, M::D, M::P);
+  wide_final<<<a.pb.B * g.G, kT, 0, st>>>(a, M::D, M::P);
   return magi_cuda_status(cudaGetLastError());
 }
 
 template <class M>
 int launch_wide(const Args& a, cudaStream_t st) {
-  return a.g.rbpc == kW ? launch_wide_t<M, true>(a, st) : launch_wide_t<M, false>(a, st);
+  const char* force = getenv("MAGI_WIDE_ROWW");   // experiment knob: 0 / 1 overrides the choice of work split
+  const bool roww = force ? (force[0] == '1' && a.g.rbpc <= kW) : a.g.rbpc == kW;
+  return roww ? launch_wide_t<M, true>(a, st) : launch_wide_t<M, false>(a, st);
 }
 
 int model_dims(int id, int& D, int& P) {
