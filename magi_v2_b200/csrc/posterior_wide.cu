@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(kT) wide_pass1(Args a) {
   double* vs = sm;                          // [np][8]
   double* red = vs + (size_t)g.np * kCh;    // [kW][4][32]
   double* ths = red + kW * 4 * 32;          // [8][P]
-  const int chunk = blockIdx.x, d = blockIdx.y, bg = blockIdx.z, b = bg / g.G, grp = bg % g.G;
+  // chain groups of a dataset are adjacent in launch order: they read the same matrix rows at the same time (L2 hits)
+  const int grp = blockIdx.x % g.G, chunk = blockIdx.x / g.G, d = blockIdx.y, b = blockIdx.z, bg = b * g.G + grp;
   const int n = a.pb.n, R = a.pb.R, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double mu_d = a.pb.mu[b * D + d];
   for (int e = tid; e < g.np * kCh; e += kT) {
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(kT) wide_pass1(Args a) {
     int lo, hi;
     jrange(g, I, lo, hi);
     double c[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 2
+#pragma unroll 4
     for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : kW) {
       const size_t t = ((size_t)I * g.nblk + J) * 64 + (lane >> 2) * 8 + (lane & 3);
       const double a0 = matC[t], a1 = matC[t + 4], m0 = matM[t], m1 = matM[t + 4];
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(kT) wide_pass2(Args a, int D) {
   const Geo& g = a.g;
   double* vs = sm;
   double* red = vs + (size_t)g.np * kCh;
-  const int chunk = blockIdx.x, d = blockIdx.y, bg = blockIdx.z, b = bg / g.G;
+  const int grp = blockIdx.x % g.G, chunk = blockIdx.x / g.G, d = blockIdx.y, b = blockIdx.z, bg = b * g.G + grp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* wsb = a.ws + (size_t)bg * g.per_bg;
   const double* Rr = wsb + off_R(g, D) + (size_t)d * g.np * kCh;
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(kT) wide_pass2(Args a, int D) {
     int lo, hi;
     jrange(g, I, lo, hi);
     double c[2] = {0.0, 0.0};
-#pragma unroll 4
+#pragma unroll 8
     for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : kW) {
       const size_t t = ((size_t)I * g.nblk + J) * 64 + (lane >> 2) * 8 + (lane & 3);
       const double a0 = matK[t], a1 = matK[t + 4];
@@ -224,7 +225,8 @@ __global__ void __launch_bounds__(kT) wide_pass3(Args a) {
   double* vs = sm;
   double* red = vs + (size_t)g.np * kCh;
   double* ths = red + kW * 4 * 32;          // [8][P]
-  const int chunk = blockIdx.x, d = blockIdx.y, bg = blockIdx.z, b = bg / g.G, grp = bg % g.G;
+  // chain groups of a dataset are adjacent in launch order: they read the same matrix rows at the same time (L2 hits)
+  const int grp = blockIdx.x % g.G, chunk = blockIdx.x / g.G, d = blockIdx.y, b = blockIdx.z, bg = b * g.G + grp;
   const int n = a.pb.n, R = a.pb.R, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* wsb = a.ws + (size_t)bg * g.per_bg;
   const double* Qall = wsb + off_Q(g, D);
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(kT) wide_pass3(Args a) {
     int lo, hi;
     jrange(g, I, lo, hi);
     double c[2] = {0.0, 0.0};
-#pragma unroll 4
+#pragma unroll 8
     for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : kW) {
       // (m^T)(I, J) = tile (J, I) transposed: A[row][k] = tile[k][row]
       const size_t t = ((size_t)J * g.nblk + I) * 64 + (lane & 3) * 8 + (lane >> 2);
@@ -347,7 +349,7 @@ int sm_count() {
 template <class M, bool ROWW>
 int launch_wide_t(const Args& a, cudaStream_t st) {
   const Geo& g = a.g;
-  const dim3 grid(g.nchunk, M::D, a.pb.B * g.G);
+  const dim3 grid(g.nchunk * g.G, M::D, a.pb.B);
   if (grid.z > 65535) return MAGI_ERR_UNSUPPORTED;
   const size_t smem = ((size_t)g.np * kCh + kW * 4 * 32 + kCh * M::P) * sizeof(double);
   if (smem > 200 * 1024) return MAGI_ERR_UNSUPPORTED;

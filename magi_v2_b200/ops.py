@@ -175,12 +175,12 @@ class PosteriorProblem:
         magi_b200_logpost_grad_wide (include/magi_b200_wide.h), every component's matrix rows spread over the grid
         -- for few.  Both compute the same function; "auto" picks by how many CTAs the first one would have.  The
         thresholds are the measured cross-overs (tools/time_wide.py, profiles/r01_notes.md): at n = 161 one CTA
-        streams its dataset in ~75 us whatever B is, the wide path needs ~30 + 2 B us; at n = 1281 the wide path
+        streams its dataset in ~75 us whatever B is, the wide path needs ~35 + B us; at n = 1281 the wide path
         wins until the CTA path can fill about half of the SMs."""
         if path == "auto":
             ctas = self.B * ((R + 7) // 8)
             npad = (self.n + 7) // 8 * 8
-            limit = 20 if npad <= 168 else (48 if npad <= 512 else 80)
+            limit = 32 if npad <= 168 else (48 if npad <= 512 else 80)
             return "wide" if ctas <= limit else "cta"
         if path not in ("cta", "wide"):
             raise ValueError("path must be 'auto', 'cta' or 'wide'")
