@@ -336,6 +336,16 @@ class FusedLeafEngine:
         self.beta_temp = None
         self._ck = None
         self._st = None
+        # per-chain state of the subtree under construction lives in buffers of fixed address, so that the leaf
+        # kernels of a doubling can be replayed as CUDA graphs (captured once per (subtree size, segment of 8 leaves))
+        self.p_sum_acc, self.p_e, self.p_H0 = mk(self.C), mk(self.C), mk(self.C)
+        self.p_n_leaf = torch.zeros(self.C, dtype=torch.int64, device=dev)
+        self.p_building = torch.zeros(self.C, dtype=torch.bool, device=dev)
+        self.p_diverged = torch.zeros(self.C, dtype=torch.bool, device=dev)
+        self.p_lu = None                                        # [C, leaves of the largest subtree] log-uniforms
+        self._graphs = {}
+        self.use_graphs = True
+        self.SEG = 8                                            # leaves per graph = leaves between early-exit checks
 
     def _stream(self):
         import ctypes as Ct
@@ -348,8 +358,17 @@ class FusedLeafEngine:
 
     def checkpoints(self, n_slots: int):
         if self._ck is None or self._ck[0].shape[0] < n_slots:
-            self._ck = tuple(torch.empty((n_slots, self.C, self.S), dtype=torch.float64, device=self.prob.device)
-                             for _ in range(2))
+            import ctypes as Ct
+            dev = self.prob.device
+            self._ck = tuple(torch.empty((n_slots, self.C, self.S), dtype=torch.float64, device=dev) for _ in range(2))
+            self.p_lu = torch.zeros((self.C, 1 << n_slots), dtype=torch.float64, device=dev)
+            ptr = lambda t: Ct.c_void_p(t.data_ptr())
+            self._st = self._lib.NutsSubtree(
+                self.C, self.nD, self.D, self.P, ptr(self.zc), ptr(self.pc), ptr(self.gc), ptr(self.rho_sub),
+                ptr(self.sub_z), ptr(self.sub_lp), ptr(self.logw_sub), ptr(self.p_sum_acc), ptr(self.p_n_leaf),
+                ptr(self.p_building), ptr(self.p_diverged), ptr(self._ck[0]), ptr(self._ck[1]), ptr(self.p_e),
+                ptr(self.p_H0))
+            self._graphs = {}                                   # captured against the old addresses
         return self._ck
 
     def value_and_grad(self, z: Tensor):
@@ -393,15 +412,12 @@ class FusedLeafEngine:
     def begin(self, sub: dict, tree: dict) -> None:
         import ctypes as Ct
         L = self._lib
-        ptr = lambda t: Ct.c_void_p(t.data_ptr())
-        for k in ("e", "H0", "log_u_leaf", "ck_p", "ck_rho", "sum_acc", "n_leaf", "building", "diverged"):
-            if not (sub[k].is_cuda and sub[k].is_contiguous()):
-                raise RuntimeError("magi_b200: the fused NUTS path needs contiguous CUDA tensors (no CPU fallback)")
-        self._st = L.NutsSubtree(self.C, self.nD, self.D, self.P, ptr(self.zc), ptr(self.pc), ptr(self.gc),
-                                 ptr(self.rho_sub), ptr(self.sub_z), ptr(self.sub_lp), ptr(self.logw_sub),
-                                 ptr(sub["sum_acc"]), ptr(sub["n_leaf"]), ptr(sub["building"]), ptr(sub["diverged"]),
-                                 ptr(sub["ck_p"]), ptr(sub["ck_rho"]), ptr(sub["e"]), ptr(sub["H0"]))
-        self._sub = sub                                         # keeps the tensors behind the raw pointers alive
+        if self._st is None or sub["ck_p"].data_ptr() != self._ck[0].data_ptr():
+            raise RuntimeError("magi_b200: the checkpoint memory must come from FusedLeafEngine.checkpoints()")
+        n_sub = sub["n_sub"]
+        self.p_e.copy_(sub["e"]); self.p_H0.copy_(sub["H0"]); self.p_building.copy_(sub["building"])
+        self.p_sum_acc.copy_(sub["sum_acc"]); self.p_n_leaf.copy_(sub["n_leaf"]); self.p_diverged.copy_(sub["diverged"])
+        self.p_lu[:, :n_sub].copy_(sub["log_u_leaf"])
         self.sub_lp.copy_(sub["lp0"])
         self.logw_sub.fill_(-math.inf)
         self._active_out = torch.zeros(self.C, dtype=torch.bool, device=self.prob.device)
@@ -410,40 +426,67 @@ class FusedLeafEngine:
             L.check(L.lib().magi_b200_nuts_subtree_begin(Ct.byref(self._st), Ct.byref(tr), self._stream()),
                     "nuts_subtree_begin")
 
-    def build_subtree(self, sub: dict) -> None:
-        """The leaves of one doubling.  Three raw C-ABI calls per leaf with pre-built argument objects (for one
-        dataset the loop is bound by launch latency, so the Python work per leaf is kept to the calls themselves)."""
+    def _launch_leaves(self, n_sub: int, i0: int, i1: int, max_energy_diff: float) -> None:
+        """Leaves [i0, i1) of a subtree of n_sub leaves on the current stream: three raw C-ABI calls per leaf."""
         import ctypes as Ct
-        L, lib, st = self._lib, self._lib.lib(), self._st
-        building, log_u_leaf, n_sub = sub["building"], sub["log_u_leaf"], sub["n_sub"]
+        L, lib = self._lib, self._lib.lib()
         ptr = lambda t: Ct.c_void_p(t.data_ptr())
         lp, gX, gs, gt = self.out
-        evalf, ws, nb = self.prob.eval_call(self.R)            # few datasets: the wide path (magi_b200_wide.h)
+        evalf, ws, nb = self.prob.eval_call(self.R)             # few datasets: the wide path (magi_b200_wide.h)
         pb = self.prob.struct(self.R)
-        st_ref, pb_ref = Ct.byref(st), Ct.byref(pb)
+        st_ref, pb_ref = Ct.byref(self._st), Ct.byref(pb)
         p_ph, p_Xn, p_sn, p_tn, p_bt = ptr(self.ph), ptr(self.Xn), ptr(self.sn), ptr(self.tn), ptr(self.bt)
         p_lp, p_gX, p_gs, p_gt, p_ws = ptr(lp), ptr(gX), ptr(gs), ptr(gt), (ptr(ws) if ws is not None else None)
-        lu0, med, sync_every = log_u_leaf.data_ptr(), float(sub["max_energy_diff"]), sub["sync_every"]
+        lu0, lu_stride = self.p_lu.data_ptr(), self.p_lu.shape[1]
         pre, post = lib.magi_b200_nuts_leaf_pre, lib.magi_b200_nuts_leaf_post
         no_slots = (Ct.c_int * 1)(0)
+        stream = self._stream()
+        for i in range(i0, i1):
+            rc = pre(st_ref, p_ph, p_Xn, p_sn, p_tn, stream)
+            rc = rc or evalf(pb_ref, p_Xn, p_sn, p_tn, p_bt, p_lp, p_gX, p_gs, p_gt, p_ws, nb, stream)
+            if i & 1:
+                t = (~i & (i + 1)).bit_length() - 1
+                slots = [bin(i - (1 << k) + 1).count("1") for k in range(1, t + 1)]
+                arr, slot_store = (Ct.c_int * t)(*slots), -1
+            else:
+                t, arr = 0, no_slots
+                slot_store = bin(i).count("1") if n_sub > 1 else -1
+            rc = rc or post(st_ref, p_ph, p_Xn, p_sn, p_tn, p_lp, p_gX, p_gs, p_gt, Ct.c_void_p(lu0 + 8 * i),
+                            lu_stride, float(max_energy_diff), slot_store, t, arr, stream)
+            if rc:
+                L.check(rc, "nuts leaf (leaf_pre / logpost_grad / leaf_post)")
+
+    def build_subtree(self, sub: dict) -> None:
+        """The leaves of one doubling, in segments of SEG leaves; between segments the host checks whether any chain
+        is still building.  A segment is a CUDA graph (captured the first time that (subtree size, segment) occurs
+        and replayed afterwards): for one dataset the loop is bound by launch latency, not by the kernels."""
+        n_sub, med = sub["n_sub"], float(sub["max_energy_diff"])
         with torch.cuda.device(self.prob.device):
-            stream = self._stream()
-            for i in range(n_sub):
-                if i % sync_every == 0 and i > 0 and not bool(building.any()):
+            self.prob.eval_call(self.R)                         # make sure the workspace exists before any capture
+            for i0 in range(0, n_sub, self.SEG):
+                if i0 > 0 and not bool(self.p_building.any()):
                     break
-                rc = pre(st_ref, p_ph, p_Xn, p_sn, p_tn, stream)
-                rc = rc or evalf(pb_ref, p_Xn, p_sn, p_tn, p_bt, p_lp, p_gX, p_gs, p_gt, p_ws, nb, stream)
-                if i & 1:
-                    t = (~i & (i + 1)).bit_length() - 1
-                    slots = [bin(i - (1 << k) + 1).count("1") for k in range(1, t + 1)]
-                    arr, slot_store = (Ct.c_int * t)(*slots), -1
-                else:
-                    t, arr = 0, no_slots
-                    slot_store = bin(i).count("1") if n_sub > 1 else -1
-                rc = rc or post(st_ref, p_ph, p_Xn, p_sn, p_tn, p_lp, p_gX, p_gs, p_gt, Ct.c_void_p(lu0 + 8 * i), n_sub,
-                                med, slot_store, t, arr, stream)
-                if rc:
-                    L.check(rc, "nuts leaf (leaf_pre / logpost_grad / leaf_post)")
+                i1 = min(n_sub, i0 + self.SEG)
+                if not self.use_graphs:
+                    self._launch_leaves(n_sub, i0, i1, med)
+                    continue
+                key = (n_sub, i0, med, self.prob.eval_path(self.R))
+                g = self._graphs.get(key)
+                if g is None:
+                    try:
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            self._launch_leaves(n_sub, i0, i1, med)
+                    except RuntimeError:
+                        # capture refused (driver / torch combination): same kernels, launched one by one
+                        self.use_graphs = False
+                        torch.cuda.synchronize(self.prob.device)
+                        self._launch_leaves(n_sub, i0, i1, med)
+                        continue
+                    self._graphs[key] = g
+                g.replay()
+        sub["sum_acc"].copy_(self.p_sum_acc); sub["n_leaf"].copy_(self.p_n_leaf); sub["diverged"].copy_(self.p_diverged)
+        sub["building"].copy_(self.p_building)
 
     def merge(self, tree: dict, log_u_acc: Tensor) -> Tensor:
         import ctypes as Ct
