@@ -336,16 +336,13 @@ class FusedLeafEngine:
         self.beta_temp = None
         self._ck = None
         self._st = None
-        # per-chain state of the subtree under construction lives in buffers of fixed address, so that the leaf
-        # kernels of a doubling can be replayed as CUDA graphs (captured once per (subtree size, segment of 8 leaves))
+        # per-chain state of the subtree under construction: fixed buffers, one argument struct for every launch
         self.p_sum_acc, self.p_e, self.p_H0 = mk(self.C), mk(self.C), mk(self.C)
         self.p_n_leaf = torch.zeros(self.C, dtype=torch.int64, device=dev)
         self.p_building = torch.zeros(self.C, dtype=torch.bool, device=dev)
         self.p_diverged = torch.zeros(self.C, dtype=torch.bool, device=dev)
         self.p_lu = None                                        # [C, leaves of the largest subtree] log-uniforms
-        self._graphs = {}
-        self.use_graphs = True
-        self.SEG = 8                                            # leaves per graph = leaves between early-exit checks
+        self.SEG = 8                                            # leaves between early-exit checks
 
     def _stream(self):
         import ctypes as Ct
@@ -368,7 +365,6 @@ class FusedLeafEngine:
                 ptr(self.sub_z), ptr(self.sub_lp), ptr(self.logw_sub), ptr(self.p_sum_acc), ptr(self.p_n_leaf),
                 ptr(self.p_building), ptr(self.p_diverged), ptr(self._ck[0]), ptr(self._ck[1]), ptr(self.p_e),
                 ptr(self.p_H0))
-            self._graphs = {}                                   # captured against the old addresses
         return self._ck
 
     def value_and_grad(self, z: Tensor):
@@ -458,33 +454,14 @@ class FusedLeafEngine:
 
     def build_subtree(self, sub: dict) -> None:
         """The leaves of one doubling, in segments of SEG leaves; between segments the host checks whether any chain
-        is still building.  A segment is a CUDA graph (captured the first time that (subtree size, segment) occurs
-        and replayed afterwards): for one dataset the loop is bound by launch latency, not by the kernels."""
+        is still building.  (Replaying the segments as CUDA graphs was measured and dropped: for one dataset a leaf is
+        bound by the six dependent kernels on the device, 47 us, not by their launches -- profiles/r01_notes.md.)"""
         n_sub, med = sub["n_sub"], float(sub["max_energy_diff"])
         with torch.cuda.device(self.prob.device):
-            self.prob.eval_call(self.R)                         # make sure the workspace exists before any capture
             for i0 in range(0, n_sub, self.SEG):
                 if i0 > 0 and not bool(self.p_building.any()):
                     break
-                i1 = min(n_sub, i0 + self.SEG)
-                if not self.use_graphs:
-                    self._launch_leaves(n_sub, i0, i1, med)
-                    continue
-                key = (n_sub, i0, med, self.prob.eval_path(self.R))
-                g = self._graphs.get(key)
-                if g is None:
-                    try:
-                        g = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g):
-                            self._launch_leaves(n_sub, i0, i1, med)
-                    except RuntimeError:
-                        # capture refused (driver / torch combination): same kernels, launched one by one
-                        self.use_graphs = False
-                        torch.cuda.synchronize(self.prob.device)
-                        self._launch_leaves(n_sub, i0, i1, med)
-                        continue
-                    self._graphs[key] = g
-                g.replay()
+                self._launch_leaves(n_sub, i0, min(n_sub, i0 + self.SEG), med)
         sub["sum_acc"].copy_(self.p_sum_acc); sub["n_leaf"].copy_(self.p_n_leaf); sub["diverged"].copy_(self.p_diverged)
         sub["building"].copy_(self.p_building)
 
