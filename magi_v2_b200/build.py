@@ -32,10 +32,17 @@ def _headers_mtime():
     return max(os.path.getmtime(h) for h in hs)
 
 
+# headers only one translation unit includes (kept out of _headers_mtime so that touching them does not rebuild
+# sampler.cu, which takes minutes)
+EXTRA_DEPS = {"nuts.cu": ["magi_b200_nuts.h"], "posterior_wide.cu": ["magi_b200_wide.h"]}
+
+
 def _compile(src, force, hm):
     obj = os.path.join(OBJ, src[:-3] + ".o")
     sp = os.path.join(CSRC, src)
-    if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(sp), hm):
+    newest = max([os.path.getmtime(sp), hm] +
+                 [os.path.getmtime(os.path.join(HERE, "..", "include", h)) for h in EXTRA_DEPS.get(src, [])])
+    if not force and os.path.exists(obj) and os.path.getmtime(obj) > newest:
         return obj, False
     cmd = [NVCC] + FLAGS + ["-c", sp, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
