@@ -174,14 +174,15 @@ class PosteriorProblem:
         """"cta": magi_b200_logpost_grad, one CTA per (dataset, 8 chains) -- for many datasets; "wide":
         magi_b200_logpost_grad_wide (include/magi_b200_wide.h), every component's matrix rows spread over the grid
         -- for few.  Both compute the same function; "auto" picks by how many CTAs the first one would have.  The
-        thresholds are the measured cross-overs (tools/time_wide.py, profiles/r01_notes.md): at n = 161 one CTA
-        streams its dataset in ~75 us whatever B is, the wide path needs ~35 + B us; at n = 1281 the wide path
-        wins until the CTA path can fill about half of the SMs."""
+        rule is the measured cross-over (tools/time_wide.py, tools/path_ab.py, profiles/r01_notes.md): at n = 161 one
+        CTA streams its dataset in ~75 us whatever B is and the wide path needs ~35 + B us, while with many datasets
+        the register-resident fast kernel of the CTA path is ~15 % ahead."""
         if path == "auto":
             ctas = self.B * ((R + 7) // 8)
             npad = (self.n + 7) // 8 * 8
-            limit = 32 if npad <= 168 else (48 if npad <= 512 else 80)
-            return "wide" if ctas <= limit else "cta"
+            # np > 168: the one-CTA-per-dataset kernels keep their vectors in a global workspace (general path) and
+            # the wide path is faster at every batch size measured (SIRW n = 321, B = 512: 1.49 vs 2.24 ms)
+            return "wide" if (npad > 168 or ctas <= 32) else "cta"
         if path not in ("cta", "wide"):
             raise ValueError("path must be 'auto', 'cta' or 'wide'")
         return path
