@@ -299,10 +299,24 @@ class PosteriorProblem:
     def hmc_run_(self, X, sig_pre, th_pre, eps, da_state, *, n_iter: int, n_leapfrog: int, iter0: int = 0,
                  num_adapt: int = 0, accum_from: int = 0, min_temp: float = 0.1, fixed_beta_temp: float = 0.0,
                  target_accept: float = 0.75, seed: int = 0, chain_id0: int = 0, keep_theta=True,
-                 keep_sigma=True, keep_X=False, X_sum: Optional[Tensor] = None, X_sumsq: Optional[Tensor] = None):
+                 keep_sigma=True, keep_X=False, X_sum: Optional[Tensor] = None, X_sumsq: Optional[Tensor] = None,
+                 path: str = "auto"):
         """Run n_iter HMC transitions in place on (X, sig_pre, th_pre, eps, da_state); returns a dict of
-        traces (thetas_samps, sigma_sqs_samps, X_samps, accept_prob, lp)."""
+        traces (thetas_samps, sigma_sqs_samps, X_samps, accept_prob, lp).  path "cta": the whole chain inside the
+        fused kernel `magi_b200_hmc_run`; "wide": one launch of the wide evaluation per leapfrog step
+        (hmc_host.py) -- same algorithm, same draws.  "auto" takes the second only for np > 168, where the wide
+        evaluation is several times faster than the fused kernel's general path; for small grids the fused kernel
+        wins even for one dataset because a whole chain costs one launch."""
         R = X.shape[1]
+        if path not in ("auto", "cta", "wide"):
+            raise ValueError("path must be 'auto', 'cta' or 'wide'")
+        if path == "wide" or (path == "auto" and (self.n + 7) // 8 * 8 > 168):
+            from .hmc_host import hmc_run_host_
+            return hmc_run_host_(self, X, sig_pre, th_pre, eps, da_state, n_iter=n_iter, n_leapfrog=n_leapfrog,
+                                 iter0=iter0, num_adapt=num_adapt, accum_from=accum_from, min_temp=min_temp,
+                                 fixed_beta_temp=fixed_beta_temp, target_accept=target_accept, seed=seed,
+                                 chain_id0=chain_id0, keep_theta=keep_theta, keep_sigma=keep_sigma, keep_X=keep_X,
+                                 X_sum=X_sum, X_sumsq=X_sumsq)
         _chk(X, "X", shape=(self.B, R, self.n, self.D)); _chk(sig_pre, "sig_pre", shape=(self.B, R, self.D))
         _chk(th_pre, "th_pre", shape=(self.B, R, self.P)); _chk(eps, "eps", shape=(self.B, R))
         _chk(da_state, "da_state", shape=(self.B, R, 4))

@@ -47,7 +47,8 @@ def test_leapfrog_trajectory_matches_oracle(model, cuda_device):
             assert abs(float(lp[b, r]) - lp1) <= 1e-9 * abs(lp1)
 
 
-def test_hmc_chain_matches_oracle_draw_for_draw(cuda_device):
+@pytest.mark.parametrize("path", ["cta", "wide"])
+def test_hmc_chain_matches_oracle_draw_for_draw(path, cuda_device):
     """Same seed, same counters: momenta, accept decisions, dual-averaged step sizes and states agree."""
     import torch
     model = "seir3"
@@ -63,8 +64,9 @@ def test_hmc_chain_matches_oracle_draw_for_draw(cuda_device):
     eps = torch.full((B, R), eps0, dtype=torch.float64, device=cuda_device)
     da = torch.zeros((B, R, 4), dtype=torch.float64, device=cuda_device)
     da[..., 2] = float(np.log(10.0 * eps0))
+    # "cta": the fused kernel; "wide": one evaluation launch per leapfrog step (hmc_host.py) -- same draws
     out = prob.hmc_run_(dX, ds, dt, eps, da, n_iter=n_iter, n_leapfrog=L, iter0=0, num_adapt=num_adapt,
-                        seed=seed, chain_id0=0, keep_X=True)
+                        seed=seed, chain_id0=0, keep_X=True, path=path)
     torch.cuda.synchronize()
     acc = out["accept_prob"].cpu().numpy()
     Xs = out["X_samps"].cpu().numpy()
@@ -105,7 +107,7 @@ def test_rng_stream_matches_oracle(cuda_device):
     dX, ds, dt = _T(X[None], cuda_device), _T(s[None], cuda_device), _T(tau[None], cuda_device)
     eps = torch.zeros((1, 8), dtype=torch.float64, device=cuda_device)
     da = torch.zeros((1, 8, 4), dtype=torch.float64, device=cuda_device)
-    out = prob.hmc_run_(dX, ds, dt, eps, da, n_iter=3, n_leapfrog=2, seed=9, num_adapt=0)
+    out = prob.hmc_run_(dX, ds, dt, eps, da, n_iter=3, n_leapfrog=2, seed=9, num_adapt=0, path="cta")
     torch.cuda.synchronize()
     assert np.allclose(dX.cpu().numpy()[0], X, rtol=0, atol=1e-15)   # (X - mu) + mu rounding only
     assert np.allclose(out["accept_prob"].cpu().numpy(), 1.0)
@@ -130,9 +132,9 @@ def test_posterior_means_within_monte_carlo_error(cuda_device):
     da = torch.zeros((1, R, 4), dtype=torch.float64, device=cuda_device)
     da[..., 2] = float(np.log(10.0 * eps0))
     prob.hmc_run_(dX, ds, dt, eps, da, n_iter=burn, n_leapfrog=L, num_adapt=240, seed=11, fixed_beta_temp=1.0,
-                  keep_theta=False, keep_sigma=False)
+                  keep_theta=False, keep_sigma=False, path="cta")
     out = prob.hmc_run_(dX, ds, dt, eps, da, n_iter=keep, n_leapfrog=L, iter0=burn, num_adapt=240, seed=11,
-                        fixed_beta_temp=1.0)
+                        fixed_beta_temp=1.0, path="cta")
     torch.cuda.synchronize()
     th_g = out["thetas_samps"].cpu().numpy()[:, 0]            # [keep, R, P]
     sg_g = out["sigma_sqs_samps"].cpu().numpy()[:, 0]
