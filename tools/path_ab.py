@@ -1,5 +1,9 @@
-import numpy as np, torch, sys
-sys.path.insert(0, "tools")
+"""A/B of the two grid shapes of the evaluation (magi_b200_logpost_grad vs magi_b200_logpost_grad_wide) at larger
+batches.  python tools/path_ab.py [sirw]"""
+import sys
+
+import numpy as np
+import torch
 from magi_v2_b200 import ops
 dev = torch.device("cuda:0")
 T = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
@@ -34,7 +38,11 @@ def run(model, D, P, n, B, R, band):
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
         print(f"{model} n={n} B={B} R={R} band={band} {path}: {ms:.3f} ms -> {B*R/ms*1e3:.3e} evals/s", flush=True)
-run("sirw", 4, 5, 321, 512, 8, None)
-run("sirw", 4, 5, 321, 512, 8, 160)
-run("lorenz96", 10, 1, 1281, 8, 8, None)
-run("seir4", 4, 3, 161, 1024, 8, 80)
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "sirw":
+        run("sirw", 4, 5, 321, 512, 8, None)
+    else:
+        run("sirw", 4, 5, 321, 512, 8, None)
+        run("sirw", 4, 5, 321, 512, 8, 160)
+        run("lorenz96", 10, 1, 1281, 8, 8, None)
+        run("seir4", 4, 3, 161, 1024, 8, 80)
