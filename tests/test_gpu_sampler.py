@@ -156,3 +156,27 @@ def test_posterior_means_within_monte_carlo_error(cuda_device):
         z = (mg.mean(axis=0) - mc.mean(axis=0)) / se
         print(nm, "cuda", mg.mean(axis=0), "oracle", mc.mean(axis=0), "z", z)
         assert np.all(np.abs(z) < 5.0), (nm, z)
+
+
+@pytest.mark.parametrize("path", ["cta", "wide"])
+def test_trajectory_moments_accumulate_from_the_requested_iteration(path, cuda_device):
+    """X_sum / X_sumsq (the posterior mean / sd of the trajectories without storing every sample) equal the sums of
+    the stored samples from `accum_from` on, for the fused kernel and for the host-driven sampler alike."""
+    import torch
+    model = "seir4"
+    c = synth_constants(model, seed=8, N=9)
+    prob = device_problem([c], model, cuda_device)
+    rng = np.random.default_rng(2)
+    R, n_iter, a0 = 4, 6, 2
+    X, s, tau = random_state(c, model, rng, R, jitter=0.005)
+    dX, ds, dt = _T(X[None], cuda_device), _T(s[None], cuda_device), _T(tau[None], cuda_device)
+    eps = torch.full((1, R), 3e-4, dtype=torch.float64, device=cuda_device)
+    da = torch.zeros((1, R, 4), dtype=torch.float64, device=cuda_device)
+    Xsum, Xsq = torch.zeros_like(dX), torch.zeros_like(dX)
+    out = prob.hmc_run_(dX, ds, dt, eps, da, n_iter=n_iter, n_leapfrog=3, seed=4, accum_from=a0, keep_X=True,
+                        X_sum=Xsum, X_sumsq=Xsq, path=path)
+    torch.cuda.synchronize()
+    Xs = out["X_samps"][a0:]
+    assert relerr(Xsum.cpu().numpy(), Xs.sum(0).cpu().numpy()) <= 1e-13
+    assert relerr(Xsq.cpu().numpy(), (Xs * Xs).sum(0).cpu().numpy()) <= 1e-13
+    assert relerr(dX.cpu().numpy(), out["X_samps"][-1].cpu().numpy()) <= 1e-15
