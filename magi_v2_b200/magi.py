@@ -102,7 +102,7 @@ class MAGI_v2:
             X_smoothed_obs = self.cv_cubic_smoother(self.I, self.X_interp_obs)                       # :192
             self.X_interp_unobs, self.thetas_init, l0, l1 = fit_unobserved(
                 self.model, self.I, X_smoothed_obs, self.observed_components, self.unobserved_components,
-                self.X_interp_obs, num_iters=self.THETA_INIT_ITERS, lr=self.ADAM_LR, seed=seed)
+                self.X_interp_obs, num_iters=self.THETA_INIT_ITERS, lr=self.ADAM_LR, seed=seed, device=self.device)
             if verbose:
                 print(f"Fitting X_unobs and theta: gradient-matching loss {l0:.4g} -> {l1:.4g}")
             hp_u = self._fit_kernel_hparams(I=self.I, X_filled=self.X_interp_unobs, verbose=verbose)  # :253
