@@ -89,3 +89,49 @@ def test_magi_batch_front_end(cuda_device):
     rn = mb.predict(num_results=10, num_burnin_steps=20, n_chains=2, seed=2, sampler="nuts", max_tree_depth=5)
     assert rn["thetas_samps"].shape == (20, 2, 10, 3) and np.isfinite(rn["thetas_samps"]).all()
     assert rn["leapfrogs_taken"].max() > 1 and rn["X_mean"].shape == (20, 161, 4)
+
+
+def test_nuts_posterior_means_within_monte_carlo_error(cuda_device):
+    """north_star: 'posterior means of theta within Monte Carlo standard error' -- for the reference's sampler.  64 NUTS
+    chains on the CUDA operator and 8 independently seeded fixed-length HMC chains of the oracle (CPU) sample the same
+    untempered posterior of a small SEIR3 problem; theta and log sigma^2 means agree within 5 combined standard errors."""
+    import torch
+    from magi_v2_b200 import nuts
+    model = "seir3"
+    c = synth_constants(model, seed=77, N=9, nan_frac=0.0)
+    prob = device_problem([c], model, cuda_device)
+    n, D, P = c.n, prob.D, prob.P
+    rng = np.random.default_rng(4)
+    R, burn, keep, eps0 = 64, 200, 400, 2e-3
+    X, s, tau = random_state(c, model, rng, R, jitter=0.005)
+    s[:] = -5.0 + 0.1 * rng.standard_normal(s.shape)
+    tau[:] = 0.5 + 0.1 * rng.standard_normal(tau.shape)
+    z = nuts.pack_state(_T(X[None], cuda_device), _T(s[None], cuda_device), _T(tau[None], cuda_device))
+    eps = torch.full((R,), eps0, dtype=torch.float64, device=cuda_device)
+    da = torch.zeros((R, 4), dtype=torch.float64, device=cuda_device)
+    da[:, 2] = float(np.log(10.0 * eps0))
+    eng = nuts.FusedLeafEngine(prob, R)
+    nuts.nuts_run_(z, eps, da, None, n_iter=burn, num_adapt=160, seed=21, fixed_beta_temp=1.0, max_tree_depth=8,
+                   leaf_engine=eng)
+    kept = []
+    out = nuts.nuts_run_(z, eps, da, None, n_iter=keep, iter0=burn, num_adapt=160, seed=21, fixed_beta_temp=1.0,
+                         max_tree_depth=8, leaf_engine=eng, on_sample=lambda it, zz, info: kept.append(zz[:, n * D:].clone()))
+    torch.cuda.synchronize()
+    tail = torch.stack(kept).cpu().numpy()                       # [keep, R, D + P]
+    assert 0.55 < float(out["accept_prob"].mean()) < 0.95 and float(out["n_leapfrog"].double().mean()) > 3
+    th_g = np.logaddexp(0, tail[:, :, D:])
+    ls_g = np.log(np.logaddexp(0, tail[:, :, :D]) + c.sigma_sqs_LB)
+    Rc, burn_c, keep_c, L = 8, 200, 400, 16
+    th_c, ls_c = [], []
+    for r in range(Rc):
+        zs, _, _, _ = mo.hmc_chain(c, model, mo.pack_state(X[r], s[r], tau[r]), burn_c + keep_c, L, eps0, seed=999,
+                                   chain_id=r, num_adaptation_steps=160, fixed_beta_temp=1.0)
+        zs = np.array(zs[burn_c:])
+        th_c.append(np.logaddexp(0, zs[:, n * D + D:]))
+        ls_c.append(np.log(np.logaddexp(0, zs[:, n * D:n * D + D]) + c.sigma_sqs_LB))
+    for g, cc, nm in ((th_g, np.array(th_c), "theta"), (ls_g, np.array(ls_c), "log sigma^2")):
+        mg, mc = g.mean(axis=0), cc.mean(axis=1)                  # per-chain means [R, k], [Rc, k]
+        se = np.sqrt(mg.var(axis=0, ddof=1) / R + mc.var(axis=0, ddof=1) / Rc)
+        zsc = (mg.mean(axis=0) - mc.mean(axis=0)) / se
+        print(nm, "nuts (cuda)", mg.mean(axis=0), "hmc (oracle)", mc.mean(axis=0), "z", zsc)
+        assert np.all(np.abs(zsc) < 5.0), (nm, zsc)
