@@ -11,12 +11,14 @@ A "step" is one log-posterior + analytic-gradient evaluation of all B*R chains (
 `magi_b200_logpost_grad`); `value` = evaluations/s with inputs resident in HBM; `e2e` = the same
 through the host-buffer entry point (pinned host -> device copies of the chain states and device ->
 host copies of lp and all gradients inside the timed region).  The `hmc` object reports HMC
-transitions/s of the fused sampler kernel (L leapfrog steps per transition) the same two ways.
+transitions/s of the fused sampler kernel (L leapfrog steps per transition) the same two ways; `nuts` the
+transitions/s and leapfrogs/s of the reference's No-U-Turn sampler on the same chains (magi_v2_b200/nuts.py on the
+fused leaf kernels); `other_configs` (rank 0, a few seconds) the evaluation throughput of BASELINE configs 2, 3, 5.
 
 The reference arm times the op-for-op restatement of the reference's TFP graph (oracle/, torch CPU
 FP64 + autograd, one chain per call as the reference does) on all host cores; TensorFlow-Probability
-itself is not installable in this image.  That is the ONLY place the oracle is executed
-by this file besides nothing else: the CUDA arm never imports it."""
+itself is not installable in this image.  The oracle is executed by this file only there and in the
+`cpu_baseline` leg of the CUDA arm (a bounded sample on rank 0); the measured CUDA path never imports it."""
 from __future__ import annotations
 
 import argparse
@@ -50,6 +52,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hmc", action="store_true")
     ap.add_argument("--no-nuts", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short evaluation-throughput lines of BASELINE configs 2, 3 and 5")
     ap.add_argument("--nuts-depth", type=int, default=4, help="max_tree_depth of the timed NUTS transitions")
     ap.add_argument("--cpu-evals-per-worker", type=int, default=24)
     return ap.parse_args()
@@ -213,6 +217,55 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------------
+def other_configs(dev):
+    """Evaluation throughput (magi_b200 log-posterior + gradient, inputs resident) on the other BASELINE.json
+    configs, which are parity-test cases rather than the bench line: synthetic constants, device-built matrices,
+    the evaluation path `PosteriorProblem.logpost_grad(path="auto")` picks.  Rank 0 only, a few seconds."""
+    import numpy as np
+    import torch
+    from magi_v2_b200 import ops
+    T = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+    res = []
+    for name, model, D, P, n, B, R, band in (("config 2: 20 SEIR datasets", "seir4", 4, 3, 161, 20, 8, 80),
+                                             ("config 3: SIRW n=321", "sirw", 4, 5, 321, 512, 8, None),
+                                             ("config 5: Lorenz-96 n=1281", "lorenz96", 10, 1, 1281, 2, 64, None)):
+        rng = np.random.default_rng(0)
+        I = np.linspace(0, 4, n)
+        phi1, phi2 = rng.uniform(0.01, 0.05, (B, D)), rng.uniform(0.15, 0.3, (B, D))
+        C_, Cp, Cpp = ops.cov_build(T(I), T(phi1), T(phi2), 2.01, True)
+        Cinv, m, Kinv, _, info = ops.factor_derive(C_, Cp, Cpp, -1 if band is None else band, 0.0)
+        ok = int(info.abs().max()) == 0
+        packed = ops.pack_matrices(Cinv, m, Kinv)
+        del C_, Cp, Cpp, Cinv, m, Kinv
+        mask = np.zeros((B, n, D), dtype=np.uint8)
+        mask[:, ::(n - 1) // 80] = 1
+        y = rng.normal(0.3, 0.1, (B, n, D)) * mask
+        prob = ops.PosteriorProblem(model, packed, mu=T(np.full((B, D), 0.3)), y=T(y), mask=T(mask, torch.uint8),
+                                    N_ds=T(np.full((B, D), 81.0)), beta=T(np.full(B, D * n / (81.0 * D))),
+                                    LB=T(np.full((B, D), 1e-6)), n=n, band=band)
+        X, s = T(rng.normal(0.3, 0.05, (B, R, n, D))), T(rng.normal(-6, 0.5, (B, R, D)))
+        tau, bt = T(rng.normal(0.5, 0.2, (B, R, P))), T(np.full((B, R), 0.37))
+        out = prob.logpost_grad_out(R)
+        for _ in range(3):
+            prob.logpost_grad(X, s, tau, bt, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            prob.logpost_grad(X, s, tau, bt, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        bytes_eval = 24.0 * D * n * n / R + 16.0 * (n * D + D + P)          # SURVEY.md section 8d
+        res.append({"config": name, "model": model, "n_grid": n, "D": D, "datasets": B, "chains_per_dataset": R,
+                    "bandsize": band, "path": prob.eval_path(R), "ms_per_launch": ms,
+                    "evals_per_s": B * R / (ms * 1e-3), "algorithmic_gb_per_s": bytes_eval * B * R / (ms * 1e-3) / 1e9,
+                    "fp64_tflops": 8.0 * D * n * n * B * R / (ms * 1e-3) / 1e12, "factorisation_ok": ok,
+                    "finite": bool(torch.isfinite(out[0]).all())})
+        del prob, packed, X, out
+    return res
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -359,6 +412,10 @@ def run_b200(args):
                             "per leaf: magi_b200_nuts_leaf_pre, magi_b200_logpost_grad, magi_b200_nuts_leaf_post"}
         del zN
 
+    others = None
+    if rank == 0 and not args.no_other_configs:
+        others = other_configs(dev)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -410,7 +467,7 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": args.steps, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "hmc": hmc, "nuts": nuts_res, "setup_s": t_setup}
+            "hmc": hmc, "nuts": nuts_res, "other_configs": others, "setup_s": t_setup}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
