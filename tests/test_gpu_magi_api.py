@@ -112,3 +112,37 @@ def test_completely_unobserved_component(cuda_device):
     assert res["X_samps"].shape == (2, 60, 161, 4) and np.isfinite(res["X_samps"]).all()
     assert np.isfinite(res["thetas_samps"]).all() and np.all(res["thetas_samps"] > 0)
     assert np.all(res["sigma_sqs_samps"] > 0)
+
+
+def test_update_kernel_matrices_for_a_forecast_grid(cuda_device):
+    """magi_v2.py:433-462: a longer grid (forecast horizon) and new hyper-parameters replace I, mag_I, beta and the
+    three banded matrix stacks; the matrices are those of the device build on the new grid."""
+    import torch
+    from magi_v2_b200 import MAGI_v2, ops
+    g = load_golden("seir_datasets.npz")
+    X = g["X_obs"][0][:, 1:].copy()
+    X[X < 0.0] = 0.0
+    model = MAGI_v2(D_thetas=3, ts_obs=g["ts_obs"], X_obs=X, bandsize=80, f_vec="seir3")
+    hp = {"phi1s": [0.0085, 0.034, 0.024], "phi2s": [0.375, 0.23, 0.109], "sigma_sqs": [1e-4, 1e-4, 1e-4]}
+    model.initial_fit(discretization=1, hparams=hp)
+    n0, beta0 = model.mag_I, model.beta
+    dt = float(model.I[1, 0] - model.I[0, 0])
+    I_new = np.concatenate([model.I.ravel(), model.I[-1, 0] + dt * np.arange(1, 41)])          # 40 more grid points
+    p1, p2 = np.array([0.01, 0.03, 0.02]), np.array([0.4, 0.25, 0.12])
+    model.update_kernel_matrices(I_new, p1, p2)
+    n1 = n0 + 40
+    assert model.mag_I == n1 and model.I.shape == (n1, 1) and np.allclose(model.phi1s, p1) and np.allclose(model.phi2s, p2)
+    assert np.isclose(model.beta, model.D * n1 / model.N_ds.sum()) and model.beta > beta0
+    for A in (model.C_d_invs, model.m_ds, model.K_d_invs):
+        assert A.shape == (3, n1, n1) and np.isfinite(A).all()
+        i, j = np.indices((n1, n1))
+        assert np.all(A[:, np.abs(i - j) > 80] == 0.0)                                           # :457-462
+    T = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=cuda_device)
+    C, Cp, Cpp = ops.cov_build(T(I_new), T(p1[None]), T(p2[None]), 2.01, False)
+    Cinv, m, Kinv, _, info = ops.factor_derive(C, Cp, Cpp, 80, 0.0)
+    assert int(info.abs().max()) == 0
+    assert np.array_equal(model.m_ds, m[0].cpu().numpy()) and np.array_equal(model.K_d_invs, Kinv[0].cpu().numpy())
+    # C^-1 really inverts C inside the band's reach: (C^-1 banded) is compared on the unbanded product of the dense one
+    Cinv_d, _, _, _, _ = ops.factor_derive(C, Cp, Cpp, -1, 0.0)
+    resid = (Cinv_d[0] @ C[0] - torch.eye(n1, dtype=torch.float64, device=cuda_device)).abs().max()
+    assert float(resid) < 1e-5
