@@ -17,6 +17,10 @@ Parity pinning status (see DESIGN.md "Oracle"):
     checked by two independent implementations (torch autograd vs. analytic
     numpy) -- the reference itself has no golden vector for it:
     "parity unpinned" for that function.
-  * leapfrog / HMC / dual averaging restate tensorflow-probability==0.24.0
-    (requirements.txt:8), which is not vendored: "parity unpinned".
+  * leapfrog / HMC / dual averaging / NUTS (``nuts_transition``: recursive,
+    single chain) restate tensorflow-probability==0.24.0 (requirements.txt:8),
+    which is not vendored: "parity unpinned".  The notebook's printed theta
+    means (vignette.ipynb:281-283) come from an earlier run of the notebook
+    (its saved predict cell ends in an exception) and do not pin this code
+    (profiles/r01_notes.md).
 """
