@@ -90,6 +90,15 @@ typedef struct {
 MAGI_API int magi_b200_nuts_momentum(uint64_t seed, const int64_t* chain_ids, uint32_t iteration, int C, int S,
                                      double* p0, magi_stream_t stream);
 
+/* `magi_b200_nuts_leaf_post` that, with next != 0, also performs the first half of the NEXT leaf's step for the chains
+ * it updates (ph <- p_new + e/2 g_new; Xn, sn, tn <- z_new + e ph): then only the first leaf of a subtree needs
+ * `magi_b200_nuts_leaf_pre`.  ph, Xn, sn, tn are read and written. */
+MAGI_API int magi_b200_nuts_leaf_post_next(const magi_nuts_subtree_t* st, double* ph, double* Xn, double* sn, double* tn,
+                                           const double* lp_new, const double* gX, const double* gs, const double* gt,
+                                           const double* log_u, int64_t log_u_stride, double max_energy_diff,
+                                           int slot_store, int n_checks, const int* check_slots /* host */, int next,
+                                           magi_stream_t stream);
+
 /* Uniform draws of the tree builder from the same stream: ua[c,k], ub[c,k] = the two (0,1) doubles of
  * Philox(counter = (index0 + k, chain_ids[c], iteration, purpose)), k < count.  purpose 2, index = doubling j: ua decides
  * the direction (ua < 1/2 = forward), ub the acceptance of the completed subtree; purpose 3, index = number of the leaf

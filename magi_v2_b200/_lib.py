@@ -73,6 +73,8 @@ _SIGNATURES = {
     "magi_b200_nuts_leaf_pre": (C.c_int, [C.POINTER(NutsSubtree)] + [C.c_void_p] * 5),
     "magi_b200_nuts_leaf_post": (C.c_int, [C.POINTER(NutsSubtree)] + [C.c_void_p] * 9 +
                                  [C.c_int64, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
+    "magi_b200_nuts_leaf_post_next": (C.c_int, [C.POINTER(NutsSubtree)] + [C.c_void_p] * 9 +
+                                      [C.c_int64, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

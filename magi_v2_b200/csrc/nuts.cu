@@ -57,9 +57,23 @@ __device__ __forceinline__ double logaddexp_d(double a, double b) {
   return m + log1p(exp(-fabs(a - b)));
 }
 
+struct PartsW {
+  double* X;
+  double* s;
+  double* t;
+};
+
+__device__ __forceinline__ void part_store(const PartsW& p, int c, int i, int nD, int D, int P, double v) {
+  if (i < nD) p.X[(size_t)c * nD + i] = v;
+  else if (i < nD + D) p.s[(size_t)c * D + (i - nD)] = v;
+  else p.t[(size_t)c * P + (i - nD - D)] = v;
+}
+
+// `next` != 0: the first half of the NEXT leaf's leapfrog step is done here as well (ph <- p + e/2 g, the position
+// parts <- z + e ph), so that only the first leaf of a subtree needs `nuts_leaf_pre_kernel`.
 template <int NCHK>
 __global__ void __launch_bounds__(kThreads, NCHK <= 2 ? 4 : 2) nuts_leaf_post_kernel(magi_nuts_subtree_t st,
-                                                                  const double* __restrict__ ph, Parts zn, Parts gn,
+                                                                  double* __restrict__ ph, PartsW zn, Parts gn, int next,
                                                                   const double* __restrict__ lp_new,
                                                                   const double* __restrict__ log_u, int64_t log_u_stride,
                                                                   double max_energy_diff, int slot_store, Checks ck) {
@@ -72,7 +86,8 @@ __global__ void __launch_bounds__(kThreads, NCHK <= 2 ? 4 : 2) nuts_leaf_post_ke
   double* pc = st.pc + row;
   double* gc = st.gc + row;
   double* rho = st.rho_sub + row;
-  const double* phc = ph + row;
+  double* phc = ph + row;
+  const double e = st.e[c];
   double* store_p = slot_store >= 0 ? st.ck_p + ((size_t)slot_store * C + c) * S : nullptr;
   double* store_r = slot_store >= 0 ? st.ck_rho + ((size_t)slot_store * C + c) * S : nullptr;
 
@@ -83,8 +98,13 @@ __global__ void __launch_bounds__(kThreads, NCHK <= 2 ? 4 : 2) nuts_leaf_post_ke
 
   for (int i = threadIdx.x; i < S; i += kThreads) {
     const double g = part_load(gn, c, i, nD, D, P);
-    const double z = part_load(zn, c, i, nD, D, P);
+    const double z = part_load(Parts{zn.X, zn.s, zn.t}, c, i, nD, D, P);
     const double p = fma(he, g, phc[i]);
+    if (next) {
+      const double h = fma(he, g, p);
+      phc[i] = h;
+      part_store(zn, c, i, nD, D, P, fma(e, h, z));
+    }
     const double r_old = rho[i];
     const double r_new = r_old + p;
     zc[i] = z;
@@ -270,6 +290,16 @@ extern "C" int magi_b200_nuts_leaf_post(const magi_nuts_subtree_t* st, const dou
                                         const double* gs, const double* gt, const double* log_u, int64_t log_u_stride,
                                         double max_energy_diff, int slot_store, int n_checks, const int* check_slots,
                                         magi_stream_t stream) {
+  return magi_b200_nuts_leaf_post_next(st, const_cast<double*>(ph), const_cast<double*>(Xn), const_cast<double*>(sn),
+                                       const_cast<double*>(tn), lp_new, gX, gs, gt, log_u, log_u_stride, max_energy_diff,
+                                       slot_store, n_checks, check_slots, 0, stream);
+}
+
+extern "C" int magi_b200_nuts_leaf_post_next(const magi_nuts_subtree_t* st, double* ph, double* Xn, double* sn,
+                                             double* tn, const double* lp_new, const double* gX, const double* gs,
+                                             const double* gt, const double* log_u, int64_t log_u_stride,
+                                             double max_energy_diff, int slot_store, int n_checks,
+                                             const int* check_slots, int next, magi_stream_t stream) {
   if (int s = check_subtree(st)) return s;
   if (!ph) return -2;
   if (!Xn) return -3;
@@ -286,10 +316,11 @@ extern "C" int magi_b200_nuts_leaf_post(const magi_nuts_subtree_t* st, const dou
   Checks ck;
   ck.n = n_checks;
   for (int k = 0; k < MAGI_NUTS_MAX_CHECKS; ++k) ck.slot[k] = k < n_checks ? check_slots[k] : 0;
-  const Parts zn{Xn, sn, tn}, gn{gX, gs, gt};
+  const PartsW zn{Xn, sn, tn};
+  const Parts gn{gX, gs, gt};
   const cudaStream_t cs = static_cast<cudaStream_t>(stream);
 #define MAGI_POST(N) \
-  nuts_leaf_post_kernel<N><<<st->C, kThreads, 0, cs>>>(*st, ph, zn, gn, lp_new, log_u, log_u_stride, max_energy_diff, \
+  nuts_leaf_post_kernel<N><<<st->C, kThreads, 0, cs>>>(*st, ph, zn, gn, next, lp_new, log_u, log_u_stride, max_energy_diff, \
                                                       slot_store, ck)
   if (n_checks == 0) MAGI_POST(0);
   else if (n_checks == 1) MAGI_POST(1);

@@ -434,11 +434,13 @@ class FusedLeafEngine:
         p_ph, p_Xn, p_sn, p_tn, p_bt = ptr(self.ph), ptr(self.Xn), ptr(self.sn), ptr(self.tn), ptr(self.bt)
         p_lp, p_gX, p_gs, p_gt, p_ws = ptr(lp), ptr(gX), ptr(gs), ptr(gt), (ptr(ws) if ws is not None else None)
         lu0, lu_stride = self.p_lu.data_ptr(), self.p_lu.shape[1]
-        pre, post = lib.magi_b200_nuts_leaf_pre, lib.magi_b200_nuts_leaf_post
+        pre, post = lib.magi_b200_nuts_leaf_pre, lib.magi_b200_nuts_leaf_post_next
         no_slots = (Ct.c_int * 1)(0)
         stream = self._stream()
         for i in range(i0, i1):
-            rc = pre(st_ref, p_ph, p_Xn, p_sn, p_tn, stream)
+            # the first half of the step: a launch of its own for the first leaf, fused into the previous leaf's
+            # `leaf_post` for the others
+            rc = pre(st_ref, p_ph, p_Xn, p_sn, p_tn, stream) if i == 0 else 0
             rc = rc or evalf(pb_ref, p_Xn, p_sn, p_tn, p_bt, p_lp, p_gX, p_gs, p_gt, p_ws, nb, stream)
             if i & 1:
                 t = (~i & (i + 1)).bit_length() - 1
@@ -448,7 +450,7 @@ class FusedLeafEngine:
                 t, arr = 0, no_slots
                 slot_store = bin(i).count("1") if n_sub > 1 else -1
             rc = rc or post(st_ref, p_ph, p_Xn, p_sn, p_tn, p_lp, p_gX, p_gs, p_gt, Ct.c_void_p(lu0 + 8 * i),
-                            lu_stride, float(max_energy_diff), slot_store, t, arr, stream)
+                            lu_stride, float(max_energy_diff), slot_store, t, arr, 1 if i + 1 < n_sub else 0, stream)
             if rc:
                 L.check(rc, "nuts leaf (leaf_pre / logpost_grad / leaf_post)")
 
