@@ -21,6 +21,7 @@ class MagiBatch:
     bandsize, model name.  Mirrors the attribute names of the reference class with a leading dataset axis."""
 
     NU = 2.01
+    THETA_INIT_LAYOUT = "reference"   # magi_v2.py:155-156 as written; see MAGI_v2._fit_thetas_init
 
     def __init__(self, ts_obs: np.ndarray, X_obs: np.ndarray, bandsize: Optional[int], model: str,
                  device: Optional[str] = None):
@@ -35,6 +36,9 @@ class MagiBatch:
         self.rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.B_total = X_obs.shape[0]
+        if self.B_total < self.world:
+            raise ValueError(f"{self.B_total} datasets cannot be sharded over {self.world} ranks: every rank needs at "
+                             "least one dataset (run with fewer ranks)")
         self.lo, self.hi = parallel.shard_range(self.B_total, self.rank, self.world)
         self.ts_obs = np.asarray(ts_obs, dtype=np.float64)
         self.X_obs = X_obs[self.lo:self.hi]                      # this rank's datasets
@@ -58,10 +62,11 @@ class MagiBatch:
                                              verbose=verbose)
         self.phi1s, self.phi2s = np.asarray(hparams["phi1s"]), np.asarray(hparams["phi2s"])
         self.sigma_sqs_init = np.asarray(hparams["sigma_sqs"])
-        self.Xhat_init = c["Xhat"]
-        self.sigma_sqs_LB = (0.01 * self.Xhat_init.std(axis=1)) ** 2                      # :299-300
+        self.X_interp = c["Xhat"]                                                         # linear interpolants, :105
+        # matrices factorised WITHOUT the band: the reference fits thetas_init on the un-banded m, K^-1 (:132-179) and
+        # applies band_part afterwards (:271-274); device_problem bands them before packing
         self.prob, info = synth.device_problem(self.model.name, c["I"], self.phi1s, self.phi2s, c["y"], c["mask"],
-                                               c["N_ds"], c["beta"], c["mu"], self.sigma_sqs_LB, self.BANDSIZE,
+                                               c["N_ds"], c["beta"], c["mu"], None, self.BANDSIZE,
                                                self.device, nu=self.NU, uniform_grid=self._uniform_grid(),
                                                keep_matrices=True)
         self.factor_info = info.cpu().numpy()
@@ -69,7 +74,28 @@ class MagiBatch:
             bad = np.argwhere(self.factor_info != 0)[:5].tolist()
             raise np.linalg.LinAlgError(f"covariance not positive definite for (dataset, component) {bad}")
         self.thetas_init = self._fit_thetas_init()
+        self.prob.kept_matrices = None
+        self.Xhat_init = self.cv_cubic_smoother(c["I"], self.X_interp)                    # :277
+        self.sigma_sqs_LB = (0.01 * self.Xhat_init.std(axis=1)) ** 2                      # :299-300
+        self.prob.set_LB(self.sigma_sqs_LB)
         return self
+
+    @staticmethod
+    def cv_cubic_smoother(I, X_filled):
+        """magi_v2.py:695-770 for all datasets at once.  The reference's cross-validation result is unused: the final
+        spline is always the least-squares cubic spline on the LARGEST knot count tried, n // 10 equally spaced
+        interior knots (:750-767; see MAGI_v2.single_cv_cubic_smoother), so one batched least-squares fit does it."""
+        from scipy.interpolate import make_lsq_spline
+        I = np.asarray(I, dtype=np.float64).reshape(-1)
+        n = I.shape[0]
+        if n < 10:
+            return X_filled
+        knot_num = n // 10
+        interior = np.linspace(I[0], I[-1], knot_num + 2)[1:-1] if knot_num > 0 else np.array([])
+        t = np.concatenate([[I[0]] * 4, interior, [I[-1]] * 4])
+        B, _, D = X_filled.shape
+        y = np.transpose(X_filled, (1, 0, 2)).reshape(n, B * D)
+        return np.transpose(make_lsq_spline(I, y, t, k=3)(I).reshape(n, B, D), (1, 0, 2))
 
     def _uniform_grid(self) -> bool:
         steps = np.diff(np.asarray(self.I, dtype=np.float64))
@@ -80,15 +106,22 @@ class MagiBatch:
         quadratic in theta for the compiled-in systems; the quadratic's coefficients come from the device
         matrices, the Adam recursion runs on the device for all datasets at once."""
         import torch
-        m, Kinv = self.prob.kept_matrices                                    # [B,D,n,n] device
+        m, Kinv = self.prob.kept_matrices                                    # [B,D,n,n] device, un-banded
         dev, B, P, D = self.device, self.B, self.model.P, self.model.D
         T = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
-        X = self.Xhat_init
+        X = self.X_interp
+        n = X.shape[1]
         f0 = np.stack([self.model.f_vec(None, X[b], np.zeros(P)) for b in range(B)])            # [B,n,D]
         F = np.stack([self.model.dtheta(None, X[b], np.zeros(P)) for b in range(B)])            # [B,n,D,P]
+        if self.THETA_INIT_LAYOUT == "reference":                                                # :155-156: a reshape
+            f0l, Fl = f0.reshape(B, D, n), F.reshape(B, D, n, P)
+        elif self.THETA_INIT_LAYOUT == "transpose":                                              # the layout of :335
+            f0l, Fl = np.transpose(f0, (0, 2, 1)), np.transpose(F, (0, 2, 1, 3))
+        else:
+            raise ValueError("THETA_INIT_LAYOUT must be 'reference' or 'transpose'")
         xc = T(np.transpose(X - self.consts["mu"][:, None], (0, 2, 1)))                          # [B,D,n]
-        r0 = T(np.transpose(f0, (0, 2, 1))) - torch.einsum("bdij,bdj->bdi", m, xc)
-        Ft = T(np.transpose(F, (0, 2, 1, 3)))                                                    # [B,D,n,P]
+        r0 = T(f0l) - torch.einsum("bdij,bdj->bdi", m, xc)
+        Ft = T(Fl)                                                                               # [B,D,n,P]
         KF = torch.einsum("bdij,bdjk->bdik", Kinv, Ft)
         KTF = torch.einsum("bdji,bdjk->bdik", Kinv, Ft)
         A = torch.einsum("bdik,bdil->bkl", Ft, KF)
@@ -106,7 +139,7 @@ class MagiBatch:
 
     def predict(self, num_results: int = 1000, num_burnin_steps: int = 1000, n_chains: int = 8,
                 n_leapfrog: int = 32, seed: int = 0, step_size: float = 0.1, keep_X_mean: bool = True,
-                gather: bool = True, sampler: str = "hmc", max_tree_depth: int = 10):
+                gather: bool = True, sampler: str = "nuts", max_tree_depth: int = 10):
         """magi_v2.py:286-425 for every dataset: returns thetas_samps [B, n_chains, num_results, P],
         sigma_sqs_samps [B, n_chains, num_results, D] (all datasets of all ranks when `gather`), the
         posterior mean / sd of the local trajectories and per-chain acceptance / step sizes.  sampler = "hmc"

@@ -35,6 +35,7 @@ class MAGI_v2:
     NU = 2.01                      # magi_v2.py:125
     ADAM_LR = 0.01                 # :161
     THETA_INIT_ITERS = 10000       # :161
+    THETA_INIT_LAYOUT = "reference"   # :155-156 as written (a reshape); "transpose" = the layout of :335
 
     def __init__(self, D_thetas: int, ts_obs: np.ndarray, X_obs: np.ndarray, bandsize: Union[int, None],
                  f_vec: Union[str, Callable, _models.OdeModel], device: str = "cuda:0"):
@@ -91,10 +92,12 @@ class MAGI_v2:
         self.Xhat_init[:, self.observed_indicators] = self.X_interp_obs
         self.mu_ds[self.observed_indicators] = self.X_interp_obs.mean(axis=0)                        # :114
         if self.D_unobserved == 0:
-            # kernel matrices on the device: replaces the per-component loop :122-128 and banding :271-274
-            self._device_kernel_matrices()
+            # kernel matrices on the device: replaces the per-component loop :122-128.  The reference fits thetas_init
+            # on the UN-banded matrices (band_part only runs at :271-274), so the band is applied afterwards.
+            self._device_kernel_matrices(band=None)
             # theta initialisation (:132-179): Adam on the t2-only objective from theta = 1
             self.thetas_init = self._fit_thetas_init()
+            self._apply_band()                                                                       # :271-274
         else:
             # :182-268 -- (thetas_init, X_unobs) jointly by gradient matching, then the GP hyper-parameters of the
             # unobserved components from the fitted trajectories, then every kernel matrix in one device call
@@ -114,7 +117,7 @@ class MAGI_v2:
             self._device_kernel_matrices()                                                           # :262-274
         self.Xhat_init = self.cv_cubic_smoother(self.I, self.Xhat_init)                              # :277
 
-    def _device_kernel_matrices(self):
+    def _device_kernel_matrices(self, band="default"):
         torch = _require_cuda()
         from . import ops
         dev = torch.device(self.device)
@@ -122,24 +125,48 @@ class MAGI_v2:
         p1 = torch.as_tensor(self.phi1s[None], dtype=torch.float64, device=dev)
         p2 = torch.as_tensor(self.phi2s[None], dtype=torch.float64, device=dev)
         C, Cp, Cpp = ops.cov_build(I, p1, p2, self.NU, False)
-        band = -1 if self.BANDSIZE is None else int(self.BANDSIZE)
-        Cinv, m, Kinv, _, info = ops.factor_derive(C, Cp, Cpp, band, 0.0)
+        if band == "default":
+            band = self.BANDSIZE
+        Cinv, m, Kinv, _, info = ops.factor_derive(C, Cp, Cpp, -1 if band is None else int(band), 0.0)
         self.factor_info = info[0].cpu().numpy()
         if np.any(self.factor_info != 0):
             raise np.linalg.LinAlgError(f"covariance not positive definite, info={self.factor_info}")
         self._dev_mats = (Cinv, m, Kinv)
         self.C_d_invs, self.m_ds, self.K_d_invs = (a[0].cpu().numpy() for a in (Cinv, m, Kinv))
 
+    def _apply_band(self):
+        """tf.linalg.band_part(., BANDSIZE, BANDSIZE) on C^-1, K^-1, m (magi_v2.py:271-274)."""
+        if self.BANDSIZE is None:
+            return
+        import torch
+        n = self.mag_I
+        i = torch.arange(n, device=self._dev_mats[0].device)
+        keep = (i[:, None] - i[None, :]).abs() <= int(self.BANDSIZE)
+        self._dev_mats = tuple(torch.where(keep, a, torch.zeros_like(a)) for a in self._dev_mats)
+        self.C_d_invs, self.m_ds, self.K_d_invs = (a[0].cpu().numpy() for a in self._dev_mats)
+
     def _fit_thetas_init(self):
-        """magi_v2.py:132-179: minimise t2(theta) = sum_d r_d^T K_d^-1 r_d with Adam (lr 0.01, 10 000
-        steps from theta = 1).  Every compiled-in right-hand side is affine in theta, so t2 is the
-        quadratic theta^T A theta - 2 b^T theta + c; Adam's iterates are reproduced on that quadratic."""
+        """magi_v2.py:132-179: minimise t2(theta) = sum_d r_d^T K_d^-1 r_d with Adam (lr 0.01, 10 000 steps from
+        theta = 1) at the linearly interpolated Xhat_init, on the un-banded matrices.  Every compiled-in right-hand side
+        is affine in theta, so t2 is the quadratic theta^T A theta - 2 b^T theta + c; Adam's iterates are reproduced
+        on that quadratic.
+
+        THETA_INIT_LAYOUT = "reference" (default) reproduces :155-156 as written: the [n, D] output of f_vec is
+        ``tf.reshape``d -- not transposed -- to (D, n, 1), which interleaves components and grid points (on the
+        vignette it drives every theta negative, so sampling starts from softplus(-5) = 0.0067, :381-382).
+        "transpose" uses the layout unnormalized_log_prob uses (:335), i.e. what the objective's comment intends."""
         X, I = self.Xhat_init, self.I
-        P = self.D_thetas
+        P, D, n = self.D_thetas, self.D, self.mag_I
         xc = (X - self.mu_ds).T                                            # [D,n]
         mx = np.einsum("dij,dj->di", self.m_ds, xc)
-        f0 = self.model.f_vec(I, X, np.zeros(P)).T                         # [D,n] part independent of theta
-        F = np.transpose(self.model.dtheta(I, X, np.zeros(P)), (1, 0, 2))  # [D,n,P]
+        f0 = self.model.f_vec(I, X, np.zeros(P))                           # [n,D] part independent of theta
+        F = self.model.dtheta(I, X, np.zeros(P))                           # [n,D,P]
+        if self.THETA_INIT_LAYOUT == "reference":
+            f0, F = f0.reshape(D, n), F.reshape(D, n, P)                   # :155-156
+        elif self.THETA_INIT_LAYOUT == "transpose":
+            f0, F = f0.T, np.transpose(F, (1, 0, 2))
+        else:
+            raise ValueError("THETA_INIT_LAYOUT must be 'reference' or 'transpose'")
         r0 = f0 - mx
         KF = np.einsum("dij,djk->dik", self.K_d_invs, F)
         KTF = np.einsum("dji,djk->dik", self.K_d_invs, F)
@@ -159,7 +186,7 @@ class MAGI_v2:
     # ------------------------------------------------------------------------------------------
     def predict(self, num_results: int = 1000, num_burnin_steps: int = 1000, sigma_sqs_LB=None, verbose=False,
                 n_chains: int = 1, n_leapfrog: int = 32, seed: int = 0, step_size: float = None,
-                init_jitter: float = 0.0, sampler: str = "hmc", max_tree_depth: int = 10,
+                init_jitter: float = 0.0, sampler: str = "nuts", max_tree_depth: int = 10,
                 beta_temp: Optional[float] = None):
         """magi_v2.py:286-425.  Returns the reference's result dictionary; with n_chains > 1 the sample
         arrays gain a leading chain axis.  sampler = "hmc": fixed-length trajectories, the whole chain inside the

@@ -143,6 +143,12 @@ class PosteriorProblem:
         self._ws = {}
         self._host = None
 
+    def set_LB(self, LB) -> None:
+        """Replace sigma_sqs_LB (magi_v2.py:299-300: it depends on the smoothed Xhat_init, known last)."""
+        LB = torch.as_tensor(LB, dtype=torch.float64, device=self.device).contiguous()
+        _chk(LB, "LB", shape=(self.B, self.D))
+        self.LB.copy_(LB)
+
     def struct(self, R: int, b0: int = 0, b1: Optional[int] = None) -> Problem:
         """magi_problem_t for datasets [b0, b1) (a view: pointers offset into the same buffers)."""
         b1 = self.B if b1 is None else b1

@@ -87,7 +87,7 @@ def device_problem(model: str, I, phi1, phi2, y, mask, N_ds, beta, mu, LB, bands
                    chunk: int = 512, uniform_grid: bool = True, keep_matrices: bool = False):
     """Kernel matrices for all datasets on the device (in chunks to bound the transient memory) and
     the PosteriorProblem that holds every constant of the log-posterior.  `keep_matrices` also keeps the
-    dense banded m and K^-1 ([B,D,n,n] each, `prob.kept_matrices`) for the theta initialisation."""
+    dense UN-banded m and K^-1 ([B,D,n,n] each, `prob.kept_matrices`) for the theta initialisation."""
     import torch
     from . import ops
     dev = torch.device(device)
@@ -100,16 +100,27 @@ def device_problem(model: str, I, phi1, phi2, y, mask, N_ds, beta, mu, LB, bands
     band = -1 if bandsize is None else int(bandsize)
     infos, kept = [], []
     per = D * 3 * npad * npad
+    keep_band = None
+    if keep_matrices and band >= 0:
+        # the theta initialisation needs the UN-banded m, K^-1 (magi_v2.py:132-179 runs before band_part, :271-274):
+        # factorise dense, keep those, then zero outside the band before packing
+        ii = torch.arange(n, device=dev)
+        keep_band = (ii[:, None] - ii[None, :]).abs() <= band
     for b0 in range(0, B, chunk):
         b1 = min(B, b0 + chunk)
         C, Cp, Cpp = ops.cov_build(I_d, p1[b0:b1].contiguous(), p2[b0:b1].contiguous(), nu, uniform_grid)
-        Cinv, m, Kinv, _, info = ops.factor_derive(C, Cp, Cpp, band, 0.0)
-        packed[b0 * per:b1 * per] = ops.pack_matrices(Cinv, m, Kinv)
-        infos.append(info)
+        Cinv, m, Kinv, _, info = ops.factor_derive(C, Cp, Cpp, -1 if keep_band is not None else band, 0.0)
         if keep_matrices:
             kept.append((m, Kinv))
+        if keep_band is not None:
+            zero = torch.zeros((), dtype=torch.float64, device=dev)
+            Cinv, m, Kinv = (torch.where(keep_band, a, zero) for a in (Cinv, m, Kinv))
+        packed[b0 * per:b1 * per] = ops.pack_matrices(Cinv, m, Kinv)
+        infos.append(info)
         del C, Cp, Cpp, Cinv, m, Kinv
     info = torch.cat(infos)
+    if LB is None:                                  # set later (PosteriorProblem.set_LB) once Xhat_init is smoothed
+        LB = np.zeros((B, D))
     prob = ops.PosteriorProblem(model, packed, mu=T(mu), y=T(y), mask=T(mask, torch.uint8), N_ds=T(N_ds),
                                 beta=T(beta), LB=T(LB), n=n, band=bandsize)
     if keep_matrices:

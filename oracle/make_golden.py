@@ -14,6 +14,11 @@ Fixtures:
   logpost_kat.npz     seeded inputs and the restated log-posterior value + autograd gradient
                       (oracle.magi_oracle) for every registry model at small n; matrices come from
                       the genuine `_build_matrices` + tf_pinv stand-in + band.
+  init_kat.npz        initial-fit stages on the vignette data (SEIR seed 0, E/I/R, discretization 1): GENUINE
+                      `cv_cubic_smoother` output (magi_v2.py:695-770); from the restatement
+                      (oracle.init_oracle; TFP / tf_keras not installable, "parity unpinned"): Fourier prior,
+                      the hyper-parameter objective and its gradient at the start, 25 Adam steps of the fit,
+                      thetas_init in both layouts (1500 Adam steps, illustrative phi).
 """
 import glob
 import os
@@ -116,6 +121,37 @@ def logpost_kat(ref):
     np.savez_compressed(os.path.join(OUT, "logpost_kat.npz"), **out)
 
 
+def init_kat(ref):
+    import torch
+    from . import init_oracle as io
+    g = np.load(os.path.join(OUT, "seir_datasets.npz"))
+    ts, X = g["ts_obs"], g["X_obs"][0][:, 1:].copy()
+    X[X < 0.0] = 0.0
+    I, Xd = mo.discretize(ts, X, 1)
+    Xi = mo.linear_interpolate(Xd)
+    out = {"X_interp": Xi, "I": I}
+    out["smoothed_genuine"] = ref.cv_cubic_smoother(I, Xi)                        # genuine reference code
+    assert np.allclose(out["smoothed_genuine"], io.cv_cubic_smoother(I, Xi), rtol=0, atol=1e-13)
+    mu2, sd2 = io.fourier_prior(Xi)
+    out["mu_phi2"], out["sd_phi2"] = mu2, sd2
+    obj = io.HparamObjective(I, Xi)
+    v = obj.initial_variables()
+    loss, grads = obj.loss_and_grads(v)
+    out["hp_v0"] = np.stack([a.detach().numpy() for a in v])                      # (phi1, phi2, sigma^2) pre-activations
+    out["hp_loss0"] = loss.numpy()                                                 # [D, D]
+    out["hp_grad0"] = np.stack([a.numpy() for a in grads])
+    trace = []
+    io.fit_kernel_hparams(I, Xi, num_iters=25, trace=trace)
+    out["hp_trace25"] = np.array([np.stack(t) for t in trace])                    # [25, 3, D]
+    phi1, phi2 = np.array([0.0085, 0.034, 0.024]), np.array([0.375, 0.23, 0.109])
+    dense = mo.kernel_matrices(I, phi1, phi2, None)
+    out["ti_phi1"], out["ti_phi2"] = phi1, phi2
+    for layout in ("reference", "transpose"):
+        out[f"thetas_init_{layout}_1500"] = io.fit_thetas_init(I, Xi, Xi.mean(axis=0), dense[1], dense[2], mo.f_seir3, 3,
+                                                               num_iters=1500, layout=layout)
+    np.savez_compressed(os.path.join(OUT, "init_kat.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = reference_object()
@@ -123,6 +159,7 @@ def main():
     grid_kat(ref)
     seir_datasets()
     logpost_kat(ref)
+    init_kat(ref)
     for f in sorted(glob.glob(os.path.join(OUT, "*.npz"))):
         print(f, os.path.getsize(f))
 
