@@ -47,7 +47,9 @@ typedef enum {
   MAGI_MODEL_SEIR3 = 0,    /* vignette.ipynb:68-79   (E,I,R; S implicit), theta=(beta,gamma,sigma) */
   MAGI_MODEL_SEIR4 = 1,    /* S explicit: BASELINE.json throughput shape D=4                        */
   MAGI_MODEL_SIRW = 2,     /* test_magi_script.py:19-45 (S,I,R,W), theta=(beta,phi,xi,chi,kappa)    */
-  MAGI_MODEL_LORENZ96 = 3  /* D=10, theta=(F)                                                       */
+  MAGI_MODEL_LORENZ96 = 3, /* D=10, theta=(F)                                                       */
+  MAGI_MODEL_USER = 100    /* a user-supplied f_vec (magi_v2.py:32-33), traced and compiled at run time into
+                              its own library built from csrc/posterior_wide.cu (magi_v2_b200/tracing.py)    */
 } magi_model_t;
 
 typedef void* magi_stream_t; /* cudaStream_t */

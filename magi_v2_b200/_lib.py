@@ -65,6 +65,7 @@ _SIGNATURES = {
                           [C.c_size_t, C.c_void_p]),
     "magi_b200_logpost_grad_wide_workspace_bytes": (C.c_size_t, [C.POINTER(Problem)]),
     "magi_b200_logpost_grad_wide": (C.c_int, [C.POINTER(Problem)] + [C.c_void_p] * 9 + [C.c_size_t, C.c_void_p]),
+    "magi_b200_probe_fp64": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "magi_b200_nuts_momentum": (C.c_int, [C.c_uint64, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "magi_b200_nuts_uniforms": (C.c_int, [C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -98,6 +99,24 @@ def lib() -> C.CDLL:
             raise RuntimeError("libmagi_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib
+
+
+_user_libs = {}
+
+
+def load_user_library(path: str) -> C.CDLL:
+    """The library tracing.build_library compiled for a user-supplied ODE system: csrc/posterior_wide.cu with the
+    generated struct, exporting the two entry points of include/magi_b200_wide.h for model id MAGI_MODEL_USER."""
+    if path not in _user_libs:
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: the traced f_vec has not been compiled (nvcc, sm_100a)")
+        L = C.CDLL(path)
+        for name in ("magi_b200_logpost_grad_wide_workspace_bytes", "magi_b200_logpost_grad_wide"):
+            res, args = _SIGNATURES[name]
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _user_libs[path] = L
+    return _user_libs[path]
 
 
 def check(status: int, what: str) -> None:

@@ -139,7 +139,8 @@ class MagiBatch:
 
     def predict(self, num_results: int = 1000, num_burnin_steps: int = 1000, n_chains: int = 8,
                 n_leapfrog: int = 32, seed: int = 0, step_size: float = 0.1, keep_X_mean: bool = True,
-                gather: bool = True, sampler: str = "nuts", max_tree_depth: int = 10):
+                gather: bool = True, sampler: str = "nuts", max_tree_depth: int = 10,
+                cached_target: bool = True):
         """magi_v2.py:286-425 for every dataset: returns thetas_samps [B, n_chains, num_results, P],
         sigma_sqs_samps [B, n_chains, num_results, D] (all datasets of all ranks when `gather`), the
         posterior mean / sd of the local trajectories and per-chain acceptance / step sizes.  sampler = "hmc"
@@ -163,7 +164,7 @@ class MagiBatch:
         cid0 = self.lo * R                                      # global chain ids: results independent of sharding
         if sampler == "nuts":
             return self._predict_nuts(X, s, tau, eps, da, num_results, num_burnin_steps, num_adapt, seed, cid0,
-                                      max_tree_depth, keep_X_mean, gather)
+                                      max_tree_depth, keep_X_mean, gather, cached_target)
         burn = self.prob.hmc_run_(X, s, tau, eps, da, n_iter=num_burnin_steps, n_leapfrog=n_leapfrog, iter0=0,
                                   num_adapt=num_adapt, seed=seed, chain_id0=cid0, keep_theta=False, keep_sigma=False)
         Xsum = torch.zeros((B, R, n, D), dtype=torch.float64, device=dev) if keep_X_mean else None
@@ -188,7 +189,7 @@ class MagiBatch:
         return res
 
     def _predict_nuts(self, X, s, tau, eps, da, num_results, num_burnin_steps, num_adapt, seed, cid0, max_tree_depth,
-                      keep_X_mean, gather):
+                      keep_X_mean, gather, cached_target=True):
         import torch
         from . import nuts
         B, R, D, P, n = self.B, X.shape[1], self.model.D, self.model.P, len(self.I)
@@ -198,7 +199,7 @@ class MagiBatch:
         eng = nuts.FusedLeafEngine(self.prob, R)
         LB = torch.as_tensor(self.sigma_sqs_LB, dtype=torch.float64, device=z.device)[:, None]
         burn = nuts.nuts_run_(z, e, d, None, n_iter=num_burnin_steps, num_adapt=num_adapt, seed=seed, chain_ids=ids,
-                              max_tree_depth=max_tree_depth, leaf_engine=eng)
+                              max_tree_depth=max_tree_depth, leaf_engine=eng, cached_target=cached_target)
         th = torch.empty((num_results, B, R, P), dtype=torch.float64, device=z.device)
         sg = torch.empty((num_results, B, R, D), dtype=torch.float64, device=z.device)
         Xsum = torch.zeros((B, R, n * D), dtype=torch.float64, device=z.device)
@@ -212,7 +213,8 @@ class MagiBatch:
                 Xsum.add_(zz[..., :n * D]); Xsq.addcmul_(zz[..., :n * D], zz[..., :n * D])
 
         out = nuts.nuts_run_(z, e, d, None, n_iter=num_results, iter0=num_burnin_steps, num_adapt=num_adapt, seed=seed,
-                             chain_ids=ids, max_tree_depth=max_tree_depth, on_sample=on_sample, leaf_engine=eng)
+                             chain_ids=ids, max_tree_depth=max_tree_depth, on_sample=on_sample, leaf_engine=eng,
+                             cached_target=cached_target)
         if gather and self.world > 1:
             sizes = parallel.shard_sizes(self.B_total, self.world)
             th = parallel.gather_samples(th, dataset_dim=1, sizes=sizes)

@@ -34,7 +34,7 @@ def _headers_mtime():
 
 # headers only one translation unit includes (kept out of _headers_mtime so that touching them does not rebuild
 # sampler.cu, which takes minutes)
-EXTRA_DEPS = {"nuts.cu": ["magi_b200_nuts.h"], "posterior_wide.cu": ["magi_b200_wide.h"]}
+EXTRA_DEPS = {"nuts.cu": ["magi_b200_nuts.h"], "posterior_wide.cu": ["magi_b200_wide.h"], "probe.cu": ["magi_b200_probe.h"]}
 
 
 def _compile(src, force, hm):

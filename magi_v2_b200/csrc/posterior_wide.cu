@@ -13,6 +13,13 @@
 #include "common.cuh"
 #include "ode_models.cuh"
 #include "../../include/magi_b200_wide.h"
+// A user-supplied ODE system (the reference's f_vec callable, magi_v2.py:32-33, :335): magi_v2_b200/tracing.py
+// traces the Python callable symbolically, writes `struct UserModel` (f and its vector-Jacobian products, as the
+// structs of ode_models.cuh) and compiles THIS file alone into a library of its own with
+//   -DMAGI_USER_MODEL_HEADER='"<path>/user_model.cuh"'
+#ifdef MAGI_USER_MODEL_HEADER
+#include MAGI_USER_MODEL_HEADER
+#endif
 
 namespace {
 
@@ -373,10 +380,14 @@ int launch_wide(const Args& a, cudaStream_t st) {
 
 int model_dims(int id, int& D, int& P) {
   switch (id) {
+#ifdef MAGI_USER_MODEL_HEADER
+    case MAGI_MODEL_USER: D = UserModel::D; P = UserModel::P; return 0;
+#else
     case MAGI_MODEL_SEIR3: D = Seir3::D; P = Seir3::P; return 0;
     case MAGI_MODEL_SEIR4: D = Seir4::D; P = Seir4::P; return 0;
     case MAGI_MODEL_SIRW: D = Sirw::D; P = Sirw::P; return 0;
     case MAGI_MODEL_LORENZ96: D = Lorenz96::D; P = Lorenz96::P; return 0;
+#endif
     default: return -1;
   }
 }
@@ -414,10 +425,14 @@ extern "C" int magi_b200_logpost_grad_wide(const magi_problem_t* pb, const doubl
   a.lp = lp; a.gX = gX; a.gsig = gsig; a.gth = gth; a.ws = static_cast<double*>(ws);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (pb->model_id) {
+#ifdef MAGI_USER_MODEL_HEADER
+    case MAGI_MODEL_USER: return launch_wide<UserModel>(a, st);
+#else
     case MAGI_MODEL_SEIR3: return launch_wide<Seir3>(a, st);
     case MAGI_MODEL_SEIR4: return launch_wide<Seir4>(a, st);
     case MAGI_MODEL_SIRW: return launch_wide<Sirw>(a, st);
     case MAGI_MODEL_LORENZ96: return launch_wide<Lorenz96>(a, st);
+#endif
     default: return MAGI_ERR_UNSUPPORTED;
   }
 }

@@ -71,7 +71,7 @@ Placement<M> placement(int n, bool with_momentum, bool with_save) {
 template <class M, bool SMEM>
 __device__ __forceinline__ void setup_scratch(Scratch<M>& S, double* ws, size_t ws_big, size_t ws_save, int n,
                                               bool with_momentum, double*& save) {
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   const int np = magi_pad8(n);
   const size_t cta = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
   double* wsc = ws ? ws + cta * (ws_big + ws_save) : nullptr;
@@ -522,11 +522,11 @@ int launch_logpost(const magi_problem_t* pb, const double* X, const double* sig_
   if constexpr (fast_model<M>()) {
     if (use_fast<M>(pb->n)) {
       const int np = magi_pad8(pb->n);
-      const size_t smem = FastScratch<M, 0>::elems(np) * sizeof(double);
+      const size_t smem = FastScratch<M, 0>::elems(np, pb->band) * sizeof(double);
       auto kern = np == kFastMaxNp ? logpost_grad_fast_kernel<M, kFastMaxNp> : logpost_grad_fast_kernel<M, 0>;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return magi_cuda_status(e);
-      kern<<<fast_grid(pb), 32 * (np / 8), smem, st>>>(*pb, X, sig_pre, th_pre, beta_temp, lp, gX, gsig, gth);
+      kern<<<fast_grid(pb), 32 * (np / 8 + kTsProd), smem, st>>>(*pb, X, sig_pre, th_pre, beta_temp, lp, gX, gsig, gth);
       return magi_cuda_status(cudaGetLastError());
     }
   }
@@ -551,13 +551,13 @@ int launch_leapfrog(const magi_problem_t* pb, double* X, double* sig_pre, double
   if constexpr (fast_model<M>()) {
     if (use_fast<M>(pb->n)) {
       const int np = magi_pad8(pb->n);
-      const size_t smem = FastScratch<M, 0>::elems(np) * sizeof(double);
+      const size_t smem = FastScratch<M, 0>::elems(np, pb->band) * sizeof(double);
       const int grid = fast_grid(pb);
       if (!ws || ws_bytes < (size_t)grid * fast_slot_elems<M>(np) * sizeof(double)) return -12;
       auto kern = np == kFastMaxNp ? leapfrog_fast_kernel<M, kFastMaxNp> : leapfrog_fast_kernel<M, 0>;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return magi_cuda_status(e);
-      kern<<<grid, 32 * (np / 8), smem, st>>>(*pb, X, sig_pre, th_pre, pX, psig, pth, eps, beta_temp, n_steps, lp_out,
+      kern<<<grid, 32 * (np / 8 + kTsProd), smem, st>>>(*pb, X, sig_pre, th_pre, pX, psig, pth, eps, beta_temp, n_steps, lp_out,
                                              static_cast<double*>(ws));
       return magi_cuda_status(cudaGetLastError());
     }
@@ -580,13 +580,13 @@ int launch_hmc(const magi_problem_t* pb, const magi_hmc_config_t* cfg, double* X
   if constexpr (fast_model<M>()) {
     if (use_fast<M>(pb->n)) {
       const int np = magi_pad8(pb->n);
-      const size_t smem = FastScratch<M, 0>::elems(np) * sizeof(double);
+      const size_t smem = FastScratch<M, 0>::elems(np, pb->band) * sizeof(double);
       const int grid = fast_grid(pb);
       if (!ws || ws_bytes < (size_t)grid * 3 * fast_slot_elems<M>(np) * sizeof(double)) return -15;
       auto kern = np == kFastMaxNp ? hmc_fast_kernel<M, kFastMaxNp> : hmc_fast_kernel<M, 0>;
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return magi_cuda_status(e);
-      kern<<<grid, 32 * (np / 8), smem, st>>>(*pb, *cfg, X, sig_pre, th_pre, eps, da_state, out,
+      kern<<<grid, 32 * (np / 8 + kTsProd), smem, st>>>(*pb, *cfg, X, sig_pre, th_pre, eps, da_state, out,
                                              static_cast<double*>(ws));
       return magi_cuda_status(cudaGetLastError());
     }
@@ -603,6 +603,13 @@ int launch_hmc(const magi_problem_t* pb, const magi_hmc_config_t* cfg, double* X
   return magi_cuda_status(cudaGetLastError());
 }
 
+#ifdef MAGI_DEV_SEIR4_ONLY   // development builds (tools/build_variant.sh): one model, compiles in a fraction of the time
+#define MAGI_DISPATCH_MODEL(id, EXPR)                  \
+  switch (id) {                                        \
+    case MAGI_MODEL_SEIR4: { using M = Seir4; EXPR; }  \
+    default: return MAGI_ERR_UNSUPPORTED;              \
+  }
+#else
 #define MAGI_DISPATCH_MODEL(id, EXPR)                  \
   switch (id) {                                        \
     case MAGI_MODEL_SEIR3: { using M = Seir3; EXPR; }  \
@@ -611,12 +618,25 @@ int launch_hmc(const magi_problem_t* pb, const magi_hmc_config_t* cfg, double* X
     case MAGI_MODEL_LORENZ96: { using M = Lorenz96; EXPR; } \
     default: return MAGI_ERR_UNSUPPORTED;              \
   }
+#endif
 
 }  // namespace
 
 extern "C" {
 
 int magi_b200_abi_version(void) { return MAGI_B200_ABI_VERSION; }
+
+#ifdef MAGI_TRACE
+// instrumented builds only (tools/trace_fast.py): fetch and reset the event timeline of CTA 0
+__attribute__((visibility("default"))) int magi_b200_debug_trace(unsigned long long* host_events, int* host_counts) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host_events, g_magi_trace, sizeof(unsigned long long) * kFastMaxBlk0 * kTraceCap);
+  cudaMemcpyFromSymbol(host_counts, g_magi_trace_n, sizeof(int) * kFastMaxBlk0);
+  int zero[kFastMaxBlk0] = {0};
+  cudaMemcpyToSymbol(g_magi_trace_n, zero, sizeof(zero));
+  return (int)cudaDeviceSynchronize();
+}
+#endif
 
 int magi_b200_model_dims(int model_id, int* D, int* P) {
   int d, p;
@@ -666,14 +686,9 @@ int magi_b200_pack_matrices(const double* Cinv, const double* m, const double* K
 }
 
 size_t magi_b200_sampler_workspace_bytes(const magi_problem_t* pb) {
-  if (!pb) return 0;
-  switch (pb->model_id) {
-    case MAGI_MODEL_SEIR3: return workspace_bytes_t<Seir3>(pb);
-    case MAGI_MODEL_SEIR4: return workspace_bytes_t<Seir4>(pb);
-    case MAGI_MODEL_SIRW: return workspace_bytes_t<Sirw>(pb);
-    case MAGI_MODEL_LORENZ96: return workspace_bytes_t<Lorenz96>(pb);
-    default: return 0;
-  }
+  int D, P;
+  if (!pb || magi_b200_model_dims(pb->model_id, &D, &P) != 0) return 0;
+  MAGI_DISPATCH_MODEL(pb->model_id, return workspace_bytes_t<M>(pb));
 }
 
 int magi_b200_logpost_grad(const magi_problem_t* pb, const double* X, const double* sig_pre,

@@ -10,59 +10,66 @@ struct HmcOut {
 };
 
 template <class M, int NP>
-__device__ __forceinline__ void fast_setup(FastScratch<M, NP>& S, int n) {
-  extern __shared__ __align__(16) double smem[];
-  S.base = smem;
+__device__ __forceinline__ void fast_setup(FastScratch<M, NP>& S, int n, int band) {
+  extern __shared__ __align__(128) double smem[];
+  S.base = smem + FastScratch<M, NP>::ring_elems(magi_pad8(n), band);   // the tile rings come first (posterior_fast.cuh)
   S.n = n;
   S.np_rt = magi_pad8(n);
 }
 
-template <class M>
-__device__ __forceinline__ bool fast_item(const magi_problem_t& pb, int item, int& b, int& nr, size_t& chain0) {
-  const int groups = (pb.R + kCh - 1) / kCh;
-  if (item >= pb.B * groups) return false;
-  b = item / groups;
-  const int r0 = (item - b * groups) * kCh;
-  nr = min(kCh, pb.R - r0);
-  chain0 = (size_t)b * pb.R + r0;
-  return true;
-}
-
-template <class M>
-__device__ __forceinline__ const double* fast_mats(const magi_problem_t& pb, int b, int np) {
-  return static_cast<const double*>(pb.packed) + (size_t)b * M::D * 3 * np * np;
+// Common start of the warp-specialised fast kernels: the consumer warps (threadIdx.x < 32 * nblk) set up their tile
+// streams; after a barrier of the whole CTA the producer warps run the copy loop and return true (the caller returns).
+template <class M, int NP>
+__device__ __forceinline__ bool fast_kernel_prologue(const FastScratch<M, NP>& S, TileStream<M>& ts, const magi_problem_t& pb,
+                                                     int evals_per_item) {
+  const bool producer = (int)(threadIdx.x >> 5) >= S.nblk();
+  if (!producer) ts_init(S, ts, pb);
+  __syncthreads();
+  if (producer) {
+#ifndef MAGI_DIAG_NOLOAD
+    ts_producer(S, pb, evals_per_item);
+#endif
+  }
+  return producer;
 }
 
 // ---- (3b) log-posterior + gradient ---------------------------------------------------------------
 template <class M, int NP>
-__global__ void __launch_bounds__(kMaxThreads, 1)
+__global__ void __launch_bounds__(kFastMaxThreads, 1)
 logpost_grad_fast_kernel(magi_problem_t pb, const double* __restrict__ X, const double* __restrict__ sig_pre,
                          const double* __restrict__ th_pre, const double* __restrict__ beta_temp,
                          double* __restrict__ lp, double* __restrict__ gX, double* __restrict__ gsig,
                          double* __restrict__ gth) {
   constexpr int D = M::D, P = M::P;
   FastScratch<M, NP> S;
-  fast_setup<M, NP>(S, pb.n);
+  fast_setup<M, NP>(S, pb.n, pb.band);
   const int n = S.n, np = S.np(), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, c2 = 2 * (lane & 3), j = warp * 8 + g;
   int b, nr;
   size_t chain0;
-  double2 a[kU];
-  if (fast_item<M>(pb, blockIdx.x, b, nr, chain0))
-    load_batch<kFwd>(a, stream_ptr<kFwd>(fast_mats<M>(pb, b, np), np, warp, lane), StepRange{0, np >> 3}, np);
+  TileStream<M> ts;
+  if (fast_kernel_prologue(S, ts, pb, 1)) return;
   for (int item = blockIdx.x; fast_item<M>(pb, item, b, nr, chain0); item += gridDim.x) {
     fast_load_item(S, pb, b, X, sig_pre, th_pre, chain0, nr);
-    int bn, nrn;
-    size_t c0n;
-    const double* next_mats = fast_item<M>(pb, item + gridDim.x, bn, nrn, c0n) ? fast_mats<M>(pb, bn, np) : nullptr;
+    {  // the next item's chain states (own elements): into L2 while this item is evaluated
+      int bn, nrn;
+      size_t c0n;
+      if (fast_item<M>(pb, item + gridDim.x, bn, nrn, c0n) && j < n) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          if (c2 + q < nrn) l2_prefetch_keep(X + ((c0n + c2 + q) * n + j) * D);
+      }
+      if (tid == 0) l2_prefetch_keep(beta_temp + chain0);   // read after the evaluation
+    }
+    const double* btv = beta_temp + chain0;
     double gxr[D][2];
-    fast_eval(S, fast_mats<M>(pb, b, np), next_mats, 1.0 / pb.beta[b], gxr, a);
+    fast_eval(S, ts, pb, b, 1.0 / pb.beta[b], gxr);
     // scale by the temperature and store in the reference layout X[n][D]
     if (j < n) {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         if (c2 + q < nr) {
-          const double bt = beta_temp[chain0 + c2 + q];
+          const double bt = btv[c2 + q];
           double* o = gX + ((chain0 + c2 + q) * n + j) * D;
 #pragma unroll
           for (int d = 0; d < D; ++d) o[d] = bt * gxr[d][q];
@@ -70,14 +77,15 @@ logpost_grad_fast_kernel(magi_problem_t pb, const double* __restrict__ X, const 
       }
     }
     if (tid < nr) {
-      const double bt = beta_temp[chain0 + tid];
+      const double bt = btv[tid];
       lp[chain0 + tid] = bt * S.L()[tid];
 #pragma unroll
       for (int d = 0; d < D; ++d) gsig[(chain0 + tid) * D + d] = bt * S.gs()[d * kCh + tid];
 #pragma unroll
       for (int k = 0; k < P; ++k) gth[(chain0 + tid) * P + k] = bt * S.gtau()[k * kCh + tid];
     }
-    __syncthreads();
+    // no barrier here: fast_eval ended with one, the stores above read registers and S.L / S.gs / S.gtau only, and
+    // the next item's loads touch none of those before the barriers of its own evaluation
   }
 }
 
@@ -108,39 +116,40 @@ __device__ __forceinline__ void fast_kick_drift(const FastScratch<M, NP>& S, dou
       }
     }
   }
-  if (tid < kCh) {
-    const double hh = ck * epsv[tid] * btv[tid], ee = epsv[tid];
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const double p = fma(hh, S.gs()[d * kCh + tid], S.ps()[d * kCh + tid]);
-      S.ps()[d * kCh + tid] = p;
-      if (drift) S.s()[d * kCh + tid] = fma(ee, p, S.s()[d * kCh + tid]);
-    }
-#pragma unroll
-    for (int k = 0; k < P; ++k) {
-      const double p = fma(hh, S.gtau()[k * kCh + tid], S.ptau()[k * kCh + tid]);
-      S.ptau()[k * kCh + tid] = p;
-      if (drift) S.tau()[k * kCh + tid] = fma(ee, p, S.tau()[k * kCh + tid]);
+  // small state parts: one thread per (parameter, chain) -- the SAME thread that transforms that parameter at the
+  // start of fast_eval, which therefore needs no barrier in between
+#pragma unroll 1
+  for (int e = tid, nthr = 32 * S.nblk(); e < (P + D) * kCh; e += nthr) {
+    const int q = e >> 3, c = e & 7;
+    const double hh = ck * epsv[c] * btv[c], ee = epsv[c];
+    if (q < P) {
+      const double p = fma(hh, S.gtau()[q * kCh + c], S.ptau()[q * kCh + c]);
+      S.ptau()[q * kCh + c] = p;
+      if (drift) S.tau()[q * kCh + c] = fma(ee, p, S.tau()[q * kCh + c]);
+    } else {
+      const int d = q - P;
+      const double p = fma(hh, S.gs()[d * kCh + c], S.ps()[d * kCh + c]);
+      S.ps()[d * kCh + c] = p;
+      if (drift) S.s()[d * kCh + c] = fma(ee, p, S.s()[d * kCh + c]);
     }
   }
 }
 
 // TFP SimpleLeapfrogIntegrator: per step  p += eps/2 g;  z += eps p;  g = grad(z);  p += eps/2 g  (the two
 // half kicks of consecutive steps are applied as one).  Needs the gradient at the current z in gxr / S.gs() /
-// S.gtau() on entry; leaves the gradient at the end point.  `next_mats`: matrices whose first fragments
-// should be in flight when the last evaluation ends (the same dataset again, the next item, or null).
+// S.gtau() on entry; leaves the gradient at the end point.
 template <class M, int NP>
-__device__ void fast_leapfrog_steps(const FastScratch<M, NP>& S, double* PX, double (&gxr)[M::D][2], double2 (&a)[kU],
-                                    const double* mats, const double* next_mats, double inv_beta,
-                                    const double* epsv, const double* btv, int n_steps) {
+__device__ void fast_leapfrog_steps(const FastScratch<M, NP>& S, TileStream<M>& ts, const magi_problem_t& pb, int b,
+                                    double* PX, double (&gxr)[M::D][2], double inv_beta, const double* epsv,
+                                    const double* btv, int n_steps) {
   if (n_steps <= 0) return;
   fast_kick_drift(S, PX, gxr, epsv, btv, 0.5, true);
   for (int st = 0; st < n_steps; ++st) {
     const bool last = st + 1 == n_steps;
-    fast_eval(S, mats, last ? next_mats : mats, inv_beta, gxr, a);  // starts with a __syncthreads-protected phase
+    fast_eval(S, ts, pb, b, inv_beta, gxr);  // starts with a __syncthreads-protected phase
     fast_kick_drift(S, PX, gxr, epsv, btv, last ? 0.5 : 1.0, !last);
   }
-  __syncthreads();
+  named_sync(32 * S.nblk());
 }
 
 // out[r] = 1/2 |p_r|^2 over all three parts (fixed summation order).  Uses S.wpart() / S.tot().
@@ -165,7 +174,7 @@ __device__ void fast_kinetic(const FastScratch<M, NP>& S, const double* PX, doub
     S.wpart()[((size_t)warp * kCh + c2) * NRED] = k0;
     S.wpart()[((size_t)warp * kCh + c2 + 1) * NRED] = k1;
   }
-  __syncthreads();
+  named_sync(32 * S.nblk());
   if (tid < kCh) {
     double t = 0.0;
 #pragma unroll 1
@@ -176,18 +185,18 @@ __device__ void fast_kinetic(const FastScratch<M, NP>& S, const double* PX, doub
     for (int k = 0; k < P; ++k) t = fma(S.ptau()[k * kCh + tid], S.ptau()[k * kCh + tid], t);
     out[tid] = 0.5 * t;
   }
-  __syncthreads();
+  named_sync(32 * S.nblk());
 }
 
 // ---- (3c) leapfrog with caller-supplied momenta ---------------------------------------------------
 template <class M, int NP>
-__global__ void __launch_bounds__(kMaxThreads, 1)
+__global__ void __launch_bounds__(kFastMaxThreads, 1)
 leapfrog_fast_kernel(magi_problem_t pb, double* X, double* sig_pre, double* th_pre, double* pX, double* psig,
                      double* pth, const double* __restrict__ eps, const double* __restrict__ beta_temp, int n_steps,
                      double* lp_out, double* ws) {
   constexpr int D = M::D, P = M::P;
   FastScratch<M, NP> S;
-  fast_setup<M, NP>(S, pb.n);
+  fast_setup<M, NP>(S, pb.n, pb.band);
   const int n = S.n, np = S.np(), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, c2 = 2 * (lane & 3), j = warp * 8 + g, nblk = np >> 3;
   double* PX = ws + (size_t)blockIdx.x * fast_slot_elems<M>(np);
@@ -195,9 +204,8 @@ leapfrog_fast_kernel(magi_problem_t pb, double* X, double* sig_pre, double* th_p
   double* btv = S.ctl() + kCh;
   int b, nr;
   size_t chain0;
-  double2 a[kU];
-  if (fast_item<M>(pb, blockIdx.x, b, nr, chain0))
-    load_batch<kFwd>(a, stream_ptr<kFwd>(fast_mats<M>(pb, b, np), np, warp, lane), StepRange{0, nblk}, np);
+  TileStream<M> ts;
+  if (fast_kernel_prologue(S, ts, pb, max(n_steps, 0) + 1)) return;
   for (int item = blockIdx.x; fast_item<M>(pb, item, b, nr, chain0); item += gridDim.x) {
     fast_load_item(S, pb, b, X, sig_pre, th_pre, chain0, nr);
     // momenta into own-element order
@@ -219,15 +227,11 @@ leapfrog_fast_kernel(magi_problem_t pb, double* X, double* sig_pre, double* th_p
 #pragma unroll
       for (int k = 0; k < P; ++k) S.ptau()[k * kCh + tid] = ok ? pth[(chain0 + tid) * P + k] : 0.0;
     }
-    __syncthreads();
-    const double* mats = fast_mats<M>(pb, b, np);
-    int bn, nrn;
-    size_t c0n;
-    const double* next_mats = fast_item<M>(pb, item + gridDim.x, bn, nrn, c0n) ? fast_mats<M>(pb, bn, np) : nullptr;
+    named_sync(32 * S.nblk());
     const double inv_beta = 1.0 / pb.beta[b];
     double gxr[D][2];
-    fast_eval(S, mats, n_steps > 0 ? mats : next_mats, inv_beta, gxr, a);
-    fast_leapfrog_steps(S, PX, gxr, a, mats, next_mats, inv_beta, epsv, btv, n_steps);
+    fast_eval(S, ts, pb, b, inv_beta, gxr);
+    fast_leapfrog_steps(S, ts, pb, b, PX, gxr, inv_beta, epsv, btv, n_steps);
 
     if (j < n) {
 #pragma unroll
@@ -256,18 +260,18 @@ leapfrog_fast_kernel(magi_problem_t pb, double* X, double* sig_pre, double* th_p
       }
       if (lp_out) lp_out[chain0 + tid] = btv[tid] * S.L()[tid];
     }
-    __syncthreads();
+    named_sync(32 * S.nblk());
   }
 }
 
 // ---- (3d) HMC sampler: all iterations of a group of 8 chains inside one CTA -------------------------
 template <class M, int NP>
-__global__ void __launch_bounds__(kMaxThreads, 1)
+__global__ void __launch_bounds__(kFastMaxThreads, 1)
 hmc_fast_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig_pre, double* th_pre, double* eps,
                 double* da_state, HmcOut out, double* ws) {
   constexpr int D = M::D, P = M::P;
   FastScratch<M, NP> S;
-  fast_setup<M, NP>(S, pb.n);
+  fast_setup<M, NP>(S, pb.n, pb.band);
   const int n = S.n, np = S.np(), tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, c2 = 2 * (lane & 3), j = warp * 8 + g, nblk = np >> 3;
   const size_t slot = fast_slot_elems<M>(np);
@@ -283,7 +287,7 @@ hmc_fast_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig
   double* accf = S.ctl() + 4 * kCh;     // [8] 1.0 = accepted
   double* L0 = S.ctl() + 5 * kCh;       // [8]
   double* da = S.ctl() + 6 * kCh;       // [4][8]
-  double* tau0 = S.ctl() + 16 * kCh;    // [P][8]
+  double* tau0 = S.ctl() + 10 * kCh;    // [P][8]
   double* gtau0 = tau0 + P * kCh;     // [P][8]
   double* s0 = gtau0 + P * kCh;       // [D][8]
   double* gs0 = s0 + D * kCh;         // [D][8]
@@ -291,9 +295,8 @@ hmc_fast_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig
 
   int b, nr;
   size_t chain0;
-  double2 a[kU];
-  if (fast_item<M>(pb, blockIdx.x, b, nr, chain0))
-    load_batch<kFwd>(a, stream_ptr<kFwd>(fast_mats<M>(pb, b, np), np, warp, lane), StepRange{0, nblk}, np);
+  TileStream<M> ts;
+  if (fast_kernel_prologue(S, ts, pb, 1 + max(cfg.n_iter, 0) * max(cfg.n_leapfrog, 0))) return;
   for (int item = blockIdx.x; fast_item<M>(pb, item, b, nr, chain0); item += gridDim.x) {
     fast_load_item(S, pb, b, X, sig_pre, th_pre, chain0, nr);
     if (tid < kCh) {
@@ -302,14 +305,10 @@ hmc_fast_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig
 #pragma unroll
       for (int q = 0; q < 4; ++q) da[q * kCh + tid] = ok ? da_state[(chain0 + tid) * 4 + q] : 0.0;
     }
-    __syncthreads();
-    const double* mats = fast_mats<M>(pb, b, np);
-    int bn, nrn;
-    size_t c0n;
-    const double* next_mats = fast_item<M>(pb, item + gridDim.x, bn, nrn, c0n) ? fast_mats<M>(pb, bn, np) : nullptr;
+    named_sync(32 * S.nblk());
     const double inv_beta = 1.0 / pb.beta[b];
     double gxr[D][2];
-    fast_eval(S, mats, cfg.n_iter > 0 ? mats : next_mats, inv_beta, gxr, a);
+    fast_eval(S, ts, pb, b, inv_beta, gxr);
 
     for (int it = 0; it < cfg.n_iter; ++it) {
       const int git = cfg.iter0 + it;
@@ -375,13 +374,12 @@ hmc_fast_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig
           for (int k = 0; k < P; ++k) S.ptau()[k * kCh + tid] = 0.0;
         }
       }
-      __syncthreads();
+      named_sync(32 * S.nblk());
       fast_kinetic(S, PX, ke);
       if (tid < kCh) h0[tid] = -bt * S.L()[tid] + ke[tid];
-      __syncthreads();
+      named_sync(32 * S.nblk());
 
-      const bool last_it = it + 1 == cfg.n_iter;
-      fast_leapfrog_steps(S, PX, gxr, a, mats, last_it ? next_mats : mats, inv_beta, epsv, btv, cfg.n_leapfrog);
+      fast_leapfrog_steps(S, ts, pb, b, PX, gxr, inv_beta, epsv, btv, cfg.n_leapfrog);
 
       fast_kinetic(S, PX, ke);
       if (tid < kCh) {
@@ -429,7 +427,7 @@ hmc_fast_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig
           }
         }
       }
-      __syncthreads();
+      named_sync(32 * S.nblk());
       // rejected chains go back to the start point; then emit the trajectory sample
       if (j < n) {
         const bool acc0 = accf[c2] != 0.0, acc1 = accf[c2 + 1] != 0.0;
@@ -457,7 +455,7 @@ hmc_fast_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig
           }
         }
       }
-      __syncthreads();
+      named_sync(32 * S.nblk());
     }
 
     // write back the chain state
@@ -480,6 +478,6 @@ hmc_fast_kernel(magi_problem_t pb, magi_hmc_config_t cfg, double* X, double* sig
 #pragma unroll
       for (int q = 0; q < 4; ++q) da_state[(chain0 + tid) * 4 + q] = da[q * kCh + tid];
     }
-    __syncthreads();
+    named_sync(32 * S.nblk());
   }
 }

@@ -46,6 +46,9 @@ def objective_and_grad(v, grid, dt, xc, loc, scale, uniform_grid: bool = False):
     C, Cp, _ = ops.cov_build(grid, phi1, phi2, NU, uniform_grid)
     S = C + (sig2 + JITTER)[..., None, None] * eye
     L, info = torch.linalg.cholesky_ex(S)
+    if int(info.abs().max()) != 0:
+        bad = torch.nonzero(info)[:4].tolist()
+        raise np.linalg.LinAlgError(f"GP covariance not positive definite for (dataset, component) {bad}")
     Sinv = torch.cholesky_inverse(L)
     a = (Sinv @ xc[..., None])[..., 0]                                          # [B,D,n]
     W = a[..., :, None] * a[..., None, :] - Sinv
@@ -91,6 +94,8 @@ def fit_kernel_hparams(I: np.ndarray, X_filled: np.ndarray, device="cuda:0", num
     b1, b2, eps = 0.9, 0.999, 1e-7                                              # tf_keras Adam defaults
     for t in range(1, num_iters + 1):
         obj, g = objective_and_grad(v, grid, dt, xc, loc, scale, uniform)
+        g = D * g          # the reference's loss is the [D, D] broadcast of :603-607 summed by tape.gradient: D x the
+                           # per-component objective (Adam is scale-free up to its epsilon; kept for step-for-step parity)
         m1 = b1 * m1 + (1 - b1) * g
         m2 = b2 * m2 + (1 - b2) * g * g
         lr_t = lr * np.sqrt(1 - b2 ** t) / (1 - b1 ** t)

@@ -6,9 +6,13 @@ log-posterior + gradient, leapfrog/HMC) running as sm_100a CUDA kernels through 
 Differences from the reference, all stated in DESIGN.md:
   * ``f_vec`` must resolve to an ODE system compiled into the library (name, OdeModel, or a callable that
     matches one when probed with numpy inputs) -- see models.py;
-  * ``predict(sampler="nuts")`` is the reference's sampler stack (NUTS trees, dual averaging, log annealing; nuts.py);
-    the default ``sampler="hmc"`` is fixed-length HMC with the same leapfrog, tempering schedule and adaptation, run
-    entirely inside one fused kernel; ``predict`` can run many chains at once (``n_chains``) and is seedable;
+  * ``predict`` runs the reference's sampler stack by default (``sampler="nuts"``: NUTS trees, dual averaging, log
+    annealing; nuts.py); ``sampler="hmc"`` is fixed-length HMC with the same leapfrog, tempering schedule and
+    adaptation, run entirely inside one fused kernel; ``predict`` can run many chains at once (``n_chains``) and is
+    seedable (the reference is unseeded);
+  * ``initial_fit`` reproduces the reference's theta initialisation AS WRITTEN (magi_v2.py:155-156 reshapes the [n, D]
+    right-hand side to (D, n, 1) instead of transposing it); ``MAGI_v2.THETA_INIT_LAYOUT = "transpose"`` selects the
+    layout the objective's comment intends;
   * C^-1 and K^-1 come from Cholesky factorisations instead of SVD pseudo-inverses;
 A CUDA device is required: there is no CPU fallback."""
 from __future__ import annotations
@@ -38,7 +42,7 @@ class MAGI_v2:
     THETA_INIT_LAYOUT = "reference"   # :155-156 as written (a reshape); "transpose" = the layout of :335
 
     def __init__(self, D_thetas: int, ts_obs: np.ndarray, X_obs: np.ndarray, bandsize: Union[int, None],
-                 f_vec: Union[str, Callable, _models.OdeModel], device: str = "cuda:0"):
+                 f_vec: Union[str, Callable, _models.OdeModel], device: str = "cuda:0", jit: Union[bool, None] = None):
         self.D_thetas = D_thetas
         self.BANDSIZE = bandsize
         self.ts_obs = np.asarray(ts_obs, dtype=np.float64)
@@ -64,7 +68,9 @@ class MAGI_v2:
         self.mu_ds = np.full((self.D,), np.nan)
         self.C_d_invs, self.m_ds, self.K_d_invs = None, None, None
         self.f_vec = f_vec
-        self.model = _models.resolve(f_vec, self.D, D_thetas)
+        # jit: None = a callable that reproduces a compiled-in system uses it, any other callable is traced and compiled
+        # at run time (tracing.py); True = always trace and compile; False = compiled-in systems only
+        self.model = _models.resolve(f_vec, self.D, D_thetas, jit=jit)
         if (self.model.D, self.model.P) != (self.D, D_thetas):
             raise ValueError(f"model {self.model.name} has D={self.model.D}, P={self.model.P}; "
                              f"data has D={self.D}, D_thetas={D_thetas}")
@@ -159,6 +165,8 @@ class MAGI_v2:
         P, D, n = self.D_thetas, self.D, self.mag_I
         xc = (X - self.mu_ds).T                                            # [D,n]
         mx = np.einsum("dij,dj->di", self.m_ds, xc)
+        if not self.model.affine_in_theta:
+            return self._fit_thetas_init_general(mx)
         f0 = self.model.f_vec(I, X, np.zeros(P))                           # [n,D] part independent of theta
         F = self.model.dtheta(I, X, np.zeros(P))                           # [n,D,P]
         if self.THETA_INIT_LAYOUT == "reference":
@@ -183,17 +191,38 @@ class MAGI_v2:
             th = th - lr_t * m1 / (np.sqrt(v1) + eps)
         return th
 
+    def _fit_thetas_init_general(self, mx):
+        """The same Adam run for a right-hand side that is not affine in theta (a traced user system): gradient of t2
+        by the chain rule through the traced d f / d theta."""
+        X, I = self.Xhat_init, self.I
+        P, D, n = self.D_thetas, self.D, self.mag_I
+        lay = (lambda a: a.reshape(D, n, *a.shape[2:])) if self.THETA_INIT_LAYOUT == "reference" else \
+            (lambda a: np.moveaxis(a, 1, 0))
+        SK = self.K_d_invs + np.transpose(self.K_d_invs, (0, 2, 1))
+        th = np.ones(P)
+        m1, v1 = np.zeros(P), np.zeros(P)
+        b1, b2a, eps = 0.9, 0.999, 1e-7
+        for t in range(1, self.THETA_INIT_ITERS + 1):
+            r = lay(self.model.f_vec(I, X, th)) - mx                       # [D,n]
+            F = lay(self.model.dtheta(I, X, th))                           # [D,n,P]
+            g = np.einsum("dik,di->k", F, np.einsum("dij,dj->di", SK, r))
+            m1 = b1 * m1 + (1 - b1) * g
+            v1 = b2a * v1 + (1 - b2a) * g * g
+            th = th - (self.ADAM_LR * np.sqrt(1 - b2a ** t) / (1 - b1 ** t)) * m1 / (np.sqrt(v1) + eps)
+        return th
+
     # ------------------------------------------------------------------------------------------
     def predict(self, num_results: int = 1000, num_burnin_steps: int = 1000, sigma_sqs_LB=None, verbose=False,
                 n_chains: int = 1, n_leapfrog: int = 32, seed: int = 0, step_size: float = None,
                 init_jitter: float = 0.0, sampler: str = "nuts", max_tree_depth: int = 10,
-                beta_temp: Optional[float] = None):
+                beta_temp: Optional[float] = None, cached_target: bool = True):
         """magi_v2.py:286-425.  Returns the reference's result dictionary; with n_chains > 1 the sample
         arrays gain a leading chain axis.  sampler = "hmc": fixed-length trajectories, the whole chain inside the
         fused CUDA kernel; sampler = "nuts": the reference's sampler (No-U-Turn trees, `nuts.py`) with one launch
         of the log-posterior + gradient kernel per leapfrog step.  beta_temp = None follows the reference's schedule
         max(1 / log(step + 2), 0.1) (:833-835, which never returns to 1); a number fixes the temperature (1.0 = the
-        untempered posterior)."""
+        untempered posterior).  cached_target (NUTS only): start every transition from the target value / gradient of
+        the previous step's temperature, as TFP's kernel results do under the reference's wrapper (nuts.nuts_run_)."""
         if sampler not in ("hmc", "nuts"):
             raise ValueError("sampler must be 'hmc' or 'nuts'")
         torch = _require_cuda()
@@ -220,7 +249,8 @@ class MAGI_v2:
         y = np.zeros(n * D); mask = np.zeros(n * D, dtype=np.uint8)
         y[self.not_nan_idxs] = self.y_tau_ds_observed
         mask[self.not_nan_idxs] = 1
-        prob = ops.PosteriorProblem(self.model.name, packed, mu=T(self.mu_ds[None]), y=T(y.reshape(1, n, D)),
+        prob = ops.PosteriorProblem(self.model if self.model.lib_path else self.model.name, packed,
+                                    mu=T(self.mu_ds[None]), y=T(y.reshape(1, n, D)),
                                     mask=T(mask.reshape(1, n, D), torch.uint8),
                                     N_ds=T(self.N_ds[None].astype(np.float64)), beta=T(np.array([self.beta])),
                                     LB=T(sigma_sqs_LB[None]), n=n, band=self.BANDSIZE)
@@ -238,7 +268,7 @@ class MAGI_v2:
         num_adapt = int(0.8 * num_burnin_steps)                                                     # :365
         if sampler == "nuts":
             return self._predict_nuts(prob, X, s, tau, eps, da, num_results, num_burnin_steps, num_adapt, seed,
-                                      sigma_sqs_LB, max_tree_depth, verbose, beta_temp)
+                                      sigma_sqs_LB, max_tree_depth, verbose, beta_temp, cached_target)
         if verbose:
             print("Starting HMC posterior sampling ...")
         start = time.time()
@@ -269,7 +299,7 @@ class MAGI_v2:
                 "minutes_elapsed": minutes}
 
     def _predict_nuts(self, prob, X, s, tau, eps, da, num_results, num_burnin_steps, num_adapt, seed, sigma_sqs_LB,
-                      max_tree_depth, verbose, beta_temp=None):
+                      max_tree_depth, verbose, beta_temp=None, cached_target=True):
         """The reference's sampler stack (magi_v2.py:357-396): NUTS in dual averaging in the annealing wrapper."""
         import torch
         from . import nuts
@@ -281,10 +311,12 @@ class MAGI_v2:
             print("Starting NUTS posterior sampling ...")
         start = time.time()
         burn = nuts.nuts_run_(z, e, d, None, n_iter=num_burnin_steps, iter0=0, num_adapt=num_adapt, seed=seed,
-                              max_tree_depth=max_tree_depth, leaf_engine=eng, fixed_beta_temp=beta_temp)
+                              max_tree_depth=max_tree_depth, leaf_engine=eng, fixed_beta_temp=beta_temp,
+                              cached_target=cached_target)
         keep = torch.empty((num_results,) + tuple(z.shape), dtype=torch.float64, device=z.device)
         out = nuts.nuts_run_(z, e, d, None, n_iter=num_results, iter0=num_burnin_steps, num_adapt=num_adapt, seed=seed,
-                             max_tree_depth=max_tree_depth, leaf_engine=eng, fixed_beta_temp=beta_temp, on_sample=lambda it, zz, info: keep[it].copy_(zz))
+                             max_tree_depth=max_tree_depth, leaf_engine=eng, fixed_beta_temp=beta_temp,
+                             cached_target=cached_target, on_sample=lambda it, zz, info: keep[it].copy_(zz))
         torch.cuda.synchronize(z.device)
         minutes = np.round((time.time() - start) / 60, 2)
         if verbose:

@@ -71,6 +71,8 @@ class OdeModel:
     dtheta: Callable       # numpy (t, X, th) -> [n,D,P]
     components: tuple
     parameters: tuple
+    lib_path: str = None   # a user system (model_id MAGI_MODEL_USER): the library tracing.build_library compiled for it
+    affine_in_theta: bool = True
 
 
 REGISTRY: Dict[str, OdeModel] = {
@@ -83,8 +85,20 @@ REGISTRY: Dict[str, OdeModel] = {
 }
 
 
-def resolve(f_vec: Union[str, OdeModel, Callable], D: int, P: int) -> OdeModel:
-    """Map the constructor's ``f_vec`` argument to a compiled-in model."""
+def user_model(f_vec: Callable, D: int, P: int) -> OdeModel:
+    """Trace a user right-hand side, generate its device code and compile its library (tracing.py; row f4)."""
+    from . import tracing
+    ts = tracing.trace(f_vec, D, P)
+    so = tracing.build_library(ts)
+    return OdeModel(f"user_{ts.source_hash}", tracing.MODEL_USER, D, P, ts.numpy_f(), ts.numpy_dtheta(),
+                    tuple(f"x{i}" for i in range(D)), tuple(f"theta{k}" for k in range(P)), lib_path=so,
+                    affine_in_theta=ts.affine_in_theta)
+
+
+def resolve(f_vec: Union[str, OdeModel, Callable], D: int, P: int, jit: Union[bool, None] = None) -> OdeModel:
+    """Map the constructor's ``f_vec`` argument to device code: a compiled-in system (name, OdeModel, or a callable
+    that reproduces one when probed), else -- or always, with jit=True -- a traced and run-time-compiled user system.
+    A callable written with ``tf.*`` ops is evaluated through the shim of tracing.py (TensorFlow itself is not needed)."""
     if isinstance(f_vec, OdeModel):
         return f_vec
     if isinstance(f_vec, str):
@@ -92,19 +106,24 @@ def resolve(f_vec: Union[str, OdeModel, Callable], D: int, P: int) -> OdeModel:
             raise KeyError(f"unknown ODE model {f_vec!r}; compiled-in models: {sorted(REGISTRY)}")
         return REGISTRY[f_vec]
     if callable(f_vec):
+        if jit:
+            return user_model(f_vec, D, P)
+        from . import tracing
         rng = np.random.default_rng(0)
         X = rng.uniform(0.05, 0.5, (7, D))
         th = rng.uniform(0.1, 2.0, P)
         t = np.linspace(0, 1, 7).reshape(-1, 1)
         try:
-            out = np.asarray(f_vec(t, X, th), dtype=np.float64)
-        except Exception as e:  # e.g. a TensorFlow callable: TF is not part of this stack
-            raise TypeError(
-                "f_vec could not be evaluated on numpy inputs; pass a registry name "
-                f"({sorted(REGISTRY)}) or an OdeModel instead") from e
-        for m in REGISTRY.values():
-            if (m.D, m.P) == (D, P) and out.shape == (7, D) and np.allclose(out, m.f_vec(t, X, th), rtol=1e-12, atol=1e-14):
-                return m
-        raise ValueError("f_vec does not match any ODE system compiled into libmagi_b200.so "
-                         f"(D={D}, P={P}); available: {sorted(REGISTRY)}")
+            out = np.asarray(tracing._rebind(f_vec)(t, X, th), dtype=np.float64)
+        except Exception:  # noqa: BLE001  (ops outside the shim: let the tracer give the precise error)
+            out = None
+        if out is not None:
+            for m in REGISTRY.values():
+                if (m.D, m.P) == (D, P) and out.shape == (7, D) and np.allclose(out, m.f_vec(t, X, th), rtol=1e-12,
+                                                                                 atol=1e-14):
+                    return m
+        if jit is False:
+            raise ValueError("f_vec does not match any ODE system compiled into libmagi_b200.so "
+                             f"(D={D}, P={P}); available: {sorted(REGISTRY)}")
+        return user_model(f_vec, D, P)
     raise TypeError("f_vec must be a model name, an OdeModel, or a callable")

@@ -155,13 +155,15 @@ def _build_subtree(sub: dict, value_and_grad) -> Tuple[Tensor, Tensor, Tensor, T
 
 def nuts_transition(z: Tensor, eps: Tensor, value_and_grad: Callable[[Tensor], Tuple[Tensor, Tensor]], seed: int,
                     chain_ids: Tensor, iteration: int, max_tree_depth: int = 10, max_energy_diff: float = 1000.0,
-                    sync_every: int = 8, leaf_engine=None) -> Dict[str, Tensor]:
+                    sync_every: int = 8, leaf_engine=None, start: Optional[Tuple[Tensor, Tensor]] = None) -> Dict[str, Tensor]:
     """z [C, S] (updated in place to the selected proposals), eps [C] step sizes, value_and_grad(z) -> (lp [C], g [C, S]).
+    `start` = (lp0 [C], g0 [C, S]): the target value / gradient at z the transition starts from (TFP keeps them in the
+    kernel results of the previous step); None evaluates them here.
     Returns accept_stat [C], n_leapfrog [C] (leaves evaluated while the chain was still building), depth [C],
     diverged [C], lp [C] (log-posterior of the new state)."""
     C, S = z.shape
     dev, f64 = z.device, torch.float64
-    lp0, g0 = value_and_grad(z)
+    lp0, g0 = value_and_grad(z) if start is None else start
     lp0, g0 = lp0.clone(), g0.clone()
     if leaf_engine is None:
         p0 = rng_normals(seed, chain_ids, iteration, S)
@@ -259,12 +261,18 @@ def nuts_run_(z: Tensor, eps: Tensor, da: Tensor,
               fixed_beta_temp: Optional[float] = None, target_accept: float = 0.75, seed: int = 0,
               chain_ids: Optional[Tensor] = None, max_tree_depth: int = 10,
               on_sample: Optional[Callable[[int, Tensor, Dict[str, Tensor]], None]] = None,
-              leaf_engine: Optional["FusedLeafEngine"] = None) -> Dict[str, Tensor]:
+              leaf_engine: Optional["FusedLeafEngine"] = None, cached_target: bool = False) -> Dict[str, Tensor]:
     """n_iter NUTS transitions in place on z [C, S], eps [C], da [C, 4].  value_and_grad_at(z, beta_temp) evaluates
     the tempered log-posterior (magi_v2.py:348) at temperature beta_temp = max(1 / log(step + 2), min_temp)
     (:833-835, :855) of the global iteration.  `on_sample(it, z, info)` is called after every transition.  With a
     `leaf_engine` (the product path: `FusedLeafEngine`) the evaluations and the per-leaf bookkeeping are the CUDA
-    kernels and `value_and_grad_at` is not used."""
+    kernels and `value_and_grad_at` is not used.
+
+    cached_target = True reproduces what the reference's wrapper does to TFP's NUTS (magi_v2.py:852-879): the rebuilt
+    kernel is handed the PREVIOUS step's kernel results, so a transition starts from the target value and gradient that
+    were computed at the previous step's temperature (TFP never re-evaluates them), while every leaf uses the new one.
+    Here that is one extra evaluation at the old temperature before the transition (same numbers, no carried state).
+    False evaluates the start point at the new temperature."""
     C = z.shape[0]
     if chain_ids is None:
         chain_ids = torch.arange(C, dtype=torch.int64, device=z.device)
@@ -275,12 +283,21 @@ def nuts_run_(z: Tensor, eps: Tensor, da: Tensor,
     for it in range(n_iter):
         g_it = iter0 + it
         bt = float(fixed_beta_temp) if fixed_beta_temp else max(1.0 / math.log(g_it + 2.0), min_temp)
+        bt_prev = bt if (fixed_beta_temp or g_it == 0) else max(1.0 / math.log(g_it + 1.0), min_temp)
+        stale = cached_target and bt_prev != bt
         if leaf_engine is not None:
+            start = None
+            if stale:
+                leaf_engine.set_beta_temp(bt_prev)
+                lp0, g0 = leaf_engine.value_and_grad(z)
+                start = (lp0.clone(), g0.clone())
             leaf_engine.set_beta_temp(bt)
             info = nuts_transition(z, eps, leaf_engine.value_and_grad, seed, chain_ids, g_it, max_tree_depth,
-                                   leaf_engine=leaf_engine)
+                                   leaf_engine=leaf_engine, start=start)
         else:
-            info = nuts_transition(z, eps, lambda zz: value_and_grad_at(zz, bt), seed, chain_ids, g_it, max_tree_depth)
+            start = value_and_grad_at(z, bt_prev) if stale else None
+            info = nuts_transition(z, eps, lambda zz: value_and_grad_at(zz, bt), seed, chain_ids, g_it, max_tree_depth,
+                                   start=start)
         dual_averaging_update_(eps, da, info["accept_stat"], num_adapt, target_accept)
         acc[it], nleap[it], lps[it], div[it] = info["accept_stat"], info["n_leapfrog"], info["lp"], info["diverged"]
         if on_sample is not None:

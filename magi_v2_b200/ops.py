@@ -121,13 +121,21 @@ class PosteriorProblem:
     """Device-resident constants of the log-posterior for B datasets (what the reference's
     ``unnormalized_log_prob`` closes over, magi_v2.py:294-300) + the ctypes view of them."""
 
-    def __init__(self, model: str, packed: Tensor, mu: Tensor, y: Tensor, mask: Tensor, N_ds: Tensor,
+    def __init__(self, model, packed: Tensor, mu: Tensor, y: Tensor, mask: Tensor, N_ds: Tensor,
                  beta: Tensor, LB: Tensor, n: int, band: Optional[int] = None):
-        self.model = model
-        self.model_id = _lib.MODEL_IDS[model]
-        D_, P_ = C.c_int(), C.c_int()
-        lib().magi_b200_model_dims(self.model_id, C.byref(D_), C.byref(P_))
-        self.D, self.P = D_.value, P_.value
+        """`model`: the name of a compiled-in system, or a models.OdeModel -- for a user system (tracing.py) the
+        evaluation runs in the library compiled for it (wide path only)."""
+        self._ulib = None
+        if isinstance(model, str):
+            self.model = model
+            self.model_id = _lib.MODEL_IDS[model]
+            D_, P_ = C.c_int(), C.c_int()
+            lib().magi_b200_model_dims(self.model_id, C.byref(D_), C.byref(P_))
+            self.D, self.P = D_.value, P_.value
+        else:
+            self.model, self.model_id, self.D, self.P = model.name, int(model.model_id), int(model.D), int(model.P)
+            if model.lib_path is not None:
+                self._ulib = _lib.load_user_library(model.lib_path)
         self.B, self.n = mu.shape[0], int(n)
         _chk(mu, "mu", shape=(self.B, self.D)); _chk(y, "y", shape=(self.B, self.n, self.D))
         _chk(mask, "mask", dtype=torch.uint8, shape=(self.B, self.n, self.D))
@@ -183,6 +191,10 @@ class PosteriorProblem:
         rule is the measured cross-over (tools/time_wide.py, tools/path_ab.py, profiles/r01_notes.md): at n = 161 one
         CTA streams its dataset in ~75 us whatever B is and the wide path needs ~35 + B us, while with many datasets
         the register-resident fast kernel of the CTA path is ~15 % ahead."""
+        if self._ulib is not None:
+            if path == "cta":
+                raise ValueError("a user-supplied ODE system runs on the wide path only")
+            return "wide"
         if path == "auto":
             ctas = self.B * ((R + 7) // 8)
             npad = (self.n + 7) // 8 * 8
@@ -199,12 +211,13 @@ class PosteriorProblem:
             ws, nb = self.workspace(R)
             return lib().magi_b200_logpost_grad, ws, nb
         pb = self.struct(R)
-        nb = lib().magi_b200_logpost_grad_wide_workspace_bytes(C.byref(pb))
+        L = self._ulib if self._ulib is not None else lib()
+        nb = L.magi_b200_logpost_grad_wide_workspace_bytes(C.byref(pb))
         ws = self._ws.get("wide")
         if ws is None or ws.numel() * 8 < nb:
             ws = torch.empty(max(nb // 8, 1), dtype=torch.float64, device=self.device)
             self._ws["wide"] = ws
-        return lib().magi_b200_logpost_grad_wide, ws, nb
+        return L.magi_b200_logpost_grad_wide, ws, nb
 
     def logpost_grad(self, X: Tensor, sig_pre: Tensor, th_pre: Tensor, beta_temp: Tensor, out=None, path: str = "auto"):
         """X [B,R,n,D], sig_pre [B,R,D], th_pre [B,R,P], beta_temp [B,R] ->
@@ -225,66 +238,40 @@ class PosteriorProblem:
         return lp, gX, gsig, gth
 
     # -- (3b) with HOST buffers: what a host-side sampler (the reference's TFP loop) would call ----------
+    def host_pipeline(self, R: int, n_chunks: int = 8, n_streams: int = 3) -> "HostPipeline":
+        """Pinned host staging + device mirrors for `logpost_grad` on HOST data (see HostPipeline)."""
+        key = (int(R), int(n_chunks), int(n_streams))
+        if self._host is None or self._host.key != key:
+            self._host = HostPipeline(self, *key)
+        return self._host
+
     def logpost_grad_host_out(self, R: int):
-        """Pinned host outputs for `logpost_grad_host`."""
-        mk = lambda *sh: torch.empty(sh, dtype=torch.float64).pin_memory()
+        """Host outputs for `logpost_grad_host`."""
+        mk = lambda *sh: torch.empty(sh, dtype=torch.float64)
         return mk(self.B, R), mk(self.B, R, self.n, self.D), mk(self.B, R, self.D), mk(self.B, R, self.P)
 
     def logpost_grad_host(self, X: Tensor, sig_pre: Tensor, th_pre: Tensor, beta_temp: Tensor, out=None,
-                          n_chunks: int = 16, n_streams: int = 4):
-        """Same as `logpost_grad` for HOST tensors (pinned for full speed): the batch is cut into
-        dataset chunks whose host->device copy, kernel launch and device->host copy are pipelined over
-        `n_streams` CUDA streams, so that PCIe in both directions overlaps the kernels.  Returns host
-        tensors (lp, gX, gsig, gth); the caller's current stream is ordered after all of it."""
+                          n_chunks: int = 8, n_streams: int = 3):
+        """`logpost_grad` for ordinary HOST tensors: copies them into the pipeline's pinned staging blocks, runs it and
+        copies the results out.  Convenience form -- a caller that wants the full PCIe rate fills
+        `host_pipeline(R).inputs(c)` in place and reads `.outputs(c)` (no host-side copies).  Returns host tensors
+        (lp, gX, gsig, gth); they are complete when the call returns."""
         R = X.shape[1]
         for t, nm, shp in ((X, "X", (self.B, R, self.n, self.D)), (sig_pre, "sig_pre", (self.B, R, self.D)),
                            (th_pre, "th_pre", (self.B, R, self.P)), (beta_temp, "beta_temp", (self.B, R))):
-            if t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous() or tuple(t.shape) != shp:
-                raise RuntimeError(f"magi_b200: {nm} must be a contiguous float64 host tensor of shape {shp}")
-        hout = self.logpost_grad_host_out(R) if out is None else out
-        with torch.cuda.device(self.device):
-            if self._host is None or self._host["R"] != R:
-                self._host = {"R": R, "in": tuple(torch.empty(t.shape, dtype=torch.float64, device=self.device)
-                                                   for t in (X, sig_pre, th_pre, beta_temp)),
-                              "out": self.logpost_grad_out(R),
-                              "streams": [torch.cuda.Stream(self.device) for _ in range(n_streams)]}
-            H = self._host
-            cur = torch.cuda.current_stream(self.device)
-            start = torch.cuda.Event()
-            start.record(cur)
-            n_chunks = max(1, min(n_chunks, self.B))
-            # equal dataset chunks (whole-wave chunks of the persistent grid measured slower: 5.7 M vs 7.5 M evals/s)
-            per = -(-self.B // n_chunks)
-            bounds = list(range(0, self.B, per)) + [self.B]
-            n_chunks = len(bounds) - 1
-            for c in range(n_chunks):
-                b0, b1 = bounds[c], bounds[c + 1]
-                if b1 == b0:
-                    continue
-                stq = H["streams"][c % len(H["streams"])]
-                stq.wait_event(start)
-                with torch.cuda.stream(stq):
-                    for d_t, h_t in zip(H["in"], (X, sig_pre, th_pre, beta_temp)):
-                        d_t[b0:b1].copy_(h_t[b0:b1], non_blocking=True)
-                    ws, nb = self.workspace(R, slot=1 + c % len(H["streams"]), n_datasets=per + 1)
-                    pb = self.struct(R, b0, b1)
-                    dX, ds, dt, dbt = (t[b0:b1] for t in H["in"])
-                    lp, gX, gs, gt = (t[b0:b1] for t in H["out"])
-                    st = lib().magi_b200_logpost_grad(C.byref(pb), _ptr(dX), _ptr(ds), _ptr(dt), _ptr(dbt), _ptr(lp),
-                                                      _ptr(gX), _ptr(gs), _ptr(gt), _ptr(ws), nb,
-                                                      C.c_void_p(stq.cuda_stream))
-                    check(st, "logpost_grad")
-                    for h_t, d_t in zip(hout, H["out"]):
-                        h_t[b0:b1].copy_(d_t[b0:b1], non_blocking=True)
-            for stq in H["streams"]:
-                ev = torch.cuda.Event()
-                ev.record(stq)
-                cur.wait_event(ev)
-        return hout
+            if t.is_cuda or t.dtype != torch.float64 or tuple(t.shape) != shp:
+                raise RuntimeError(f"magi_b200: {nm} must be a float64 host tensor of shape {shp}")
+        hp = self.host_pipeline(R, n_chunks, n_streams)
+        hp.fill(X, sig_pre, th_pre, beta_temp)
+        hp.run()
+        return hp.gather(out)
 
     # -- (3c) ------------------------------------------------------------------------------------
     def leapfrog_(self, X, sig_pre, th_pre, pX, psig, pth, eps, beta_temp, n_steps: int):
         """In-place leapfrog trajectory with the given momenta; returns lp at the end point."""
+        if self._ulib is not None:
+            raise NotImplementedError("the fused leapfrog kernel exists for the compiled-in systems; a user-supplied "
+                                      "system samples through hmc_run_ / nuts (one evaluation launch per step)")
         R = X.shape[1]
         for t, nm, shp in ((X, "X", (self.B, R, self.n, self.D)), (pX, "pX", (self.B, R, self.n, self.D)),
                            (sig_pre, "sig_pre", (self.B, R, self.D)), (psig, "psig", (self.B, R, self.D)),
@@ -316,7 +303,7 @@ class PosteriorProblem:
         R = X.shape[1]
         if path not in ("auto", "cta", "wide"):
             raise ValueError("path must be 'auto', 'cta' or 'wide'")
-        if path == "wide" or (path == "auto" and (self.n + 7) // 8 * 8 > 168):
+        if self._ulib is not None or path == "wide" or (path == "auto" and (self.n + 7) // 8 * 8 > 168):
             from .hmc_host import hmc_run_host_
             return hmc_run_host_(self, X, sig_pre, th_pre, eps, da_state, n_iter=n_iter, n_leapfrog=n_leapfrog,
                                  iter0=iter0, num_adapt=num_adapt, accum_from=accum_from, min_temp=min_temp,
@@ -348,6 +335,105 @@ class PosteriorProblem:
 # ------------------------------------------------------------------------------------------------
 # (3b) as a registered operator (functional form; the class above is the stateful convenience)
 # ------------------------------------------------------------------------------------------------
+class HostPipeline:
+    """`magi_b200_logpost_grad` for chain states that live in HOST memory (the position of a host-side sampler such as
+    the reference's TFP loop, which calls its target once per leapfrog step, magi_v2.py:362).
+
+    The batch is cut into `n_chunks` dataset chunks.  Every chunk owns ONE contiguous pinned input block
+    [X | sig_pre | th_pre | beta_temp] and ONE contiguous pinned output block [lp | gX | gsig | gth], mirrored on the
+    device, so that a chunk costs exactly one host->device copy, one kernel launch and one device->host copy;
+    chunks are pipelined over `n_streams` CUDA streams (both PCIe directions and the kernels overlap).
+    `inputs(c)` / `outputs(c)` are views into the pinned blocks: fill / read them in place.  `run()` returns when
+    every output block is complete on the host."""
+
+    def __init__(self, prob: "PosteriorProblem", R: int, n_chunks: int, n_streams: int):
+        self.prob, self.R, self.key = prob, R, (R, n_chunks, n_streams)
+        B, n, D, P = prob.B, prob.n, prob.D, prob.P
+        n_chunks = max(1, min(n_chunks, B))
+        per = -(-B // n_chunks)
+        self.bounds = [(b0, min(B, b0 + per)) for b0 in range(0, B, per)]
+        self.shapes = lambda nb: ((nb, R, n, D), (nb, R, D), (nb, R, P), (nb, R))
+        self.oshapes = lambda nb: ((nb, R), (nb, R, n, D), (nb, R, D), (nb, R, P))
+        per_chain = n * D + D + P + 1
+        self.offsets = [b0 * R * per_chain for b0, _ in self.bounds] + [B * R * per_chain]
+        total = B * R * per_chain
+        self.h_in = torch.empty(total, dtype=torch.float64).pin_memory()
+        self.h_out = torch.empty(total, dtype=torch.float64).pin_memory()
+        with torch.cuda.device(prob.device):
+            self.d_in = torch.empty(total, dtype=torch.float64, device=prob.device)
+            self.d_out = torch.empty(total, dtype=torch.float64, device=prob.device)
+            self.streams = [torch.cuda.Stream(prob.device) for _ in range(max(1, n_streams))]
+        self.done = torch.cuda.Event()
+        self.h2d_bytes = self.d2h_bytes = total * 8
+
+    @staticmethod
+    def _views(flat: Tensor, off: int, shapes):
+        out = []
+        for sh in shapes:
+            k = 1
+            for v in sh:
+                k *= v
+            out.append(flat[off:off + k].view(sh))
+            off += k
+        return tuple(out)
+
+    @property
+    def n_chunks(self) -> int:
+        return len(self.bounds)
+
+    def inputs(self, c: int):
+        """(X, sig_pre, th_pre, beta_temp) of chunk c: pinned host views, datasets bounds[c][0] .. bounds[c][1]."""
+        b0, b1 = self.bounds[c]
+        return self._views(self.h_in, self.offsets[c], self.shapes(b1 - b0))
+
+    def outputs(self, c: int):
+        """(lp, gX, gsig, gth) of chunk c: pinned host views."""
+        b0, b1 = self.bounds[c]
+        return self._views(self.h_out, self.offsets[c], self.oshapes(b1 - b0))
+
+    def fill(self, X: Tensor, sig_pre: Tensor, th_pre: Tensor, beta_temp: Tensor) -> None:
+        for c, (b0, b1) in enumerate(self.bounds):
+            for dst, src in zip(self.inputs(c), (X, sig_pre, th_pre, beta_temp)):
+                dst.copy_(src[b0:b1])
+
+    def gather(self, out=None):
+        out = self.prob.logpost_grad_host_out(self.R) if out is None else out
+        for c, (b0, b1) in enumerate(self.bounds):
+            for dst, src in zip(out, self.outputs(c)):
+                dst[b0:b1].copy_(src)
+        return out
+
+    def run(self, wait: bool = True) -> None:
+        prob, R = self.prob, self.R
+        with torch.cuda.device(prob.device):
+            cur = torch.cuda.current_stream(prob.device)
+            start = torch.cuda.Event()
+            start.record(cur)
+            per = self.bounds[0][1] - self.bounds[0][0]
+            for c, (b0, b1) in enumerate(self.bounds):
+                stq = self.streams[c % len(self.streams)]
+                stq.wait_event(start)
+                o0, o1 = self.offsets[c], self.offsets[c + 1]
+                with torch.cuda.stream(stq):
+                    self.d_in[o0:o1].copy_(self.h_in[o0:o1], non_blocking=True)           # one H2D
+                    dX, ds, dt, dbt = self._views(self.d_in, o0, self.shapes(b1 - b0))
+                    lp, gX, gs, gt = self._views(self.d_out, o0, self.oshapes(b1 - b0))
+                    ws, nb = prob.workspace(R, slot=1 + c % len(self.streams), n_datasets=per)
+                    pb = prob.struct(R, b0, b1)
+                    st = lib().magi_b200_logpost_grad(C.byref(pb), _ptr(dX), _ptr(ds), _ptr(dt), _ptr(dbt), _ptr(lp),
+                                                      _ptr(gX), _ptr(gs), _ptr(gt), _ptr(ws), nb,
+                                                      C.c_void_p(stq.cuda_stream))
+                    check(st, "logpost_grad")
+                    self.h_out[o0:o1].copy_(self.d_out[o0:o1], non_blocking=True)         # one D2H
+            for stq in self.streams:
+                ev = torch.cuda.Event()
+                ev.record(stq)
+                cur.wait_event(ev)
+            self.done.record(cur)
+        if wait:
+            self.done.synchronize()
+
+
 @torch.library.custom_op("magi_b200::logpost_grad", mutates_args=(), device_types="cuda")
 def logpost_grad(model_id: int, X: Tensor, sig_pre: Tensor, th_pre: Tensor, beta_temp: Tensor, packed: Tensor,
                  mu: Tensor, y: Tensor, mask: Tensor, N_ds: Tensor, beta: Tensor, LB: Tensor, band: int = -1) -> Tuple[Tensor, Tensor, Tensor, Tensor]:

@@ -149,4 +149,5 @@ def sweep_problem(B: int, R: int, device, seed0: int = 0, model: str = "seir4", 
     th0 = data["thetas_true"] * np.exp(rng.uniform(-0.1, 0.1, data["thetas_true"].shape))
     tau0 = np.log(np.expm1(th0))
     state = {"X": X0, "sig_pre": np.repeat(s0[:, None], R, axis=1), "th_pre": np.repeat(tau0[:, None], R, axis=1)}
+    data.update(phi1=phi1, phi2=phi2, LB=LB, consts=c, bandsize=bandsize)     # what a checker needs to rebuild a dataset
     return prob, info, state, data

@@ -442,7 +442,13 @@ void mo_nuts_chain(const mo_problem *h, const double *z0, int n_iter, double eps
     c.bt = bt; c.eps = da.eps; c.iter = (uint32_t)(step0 + it);
     double lp0;
     if (cached_lp && have_cache) lp0 = lp_cache;            /* g0 already holds the cached gradient */
-    else lp0 = logpost_grad(h, z, bt, g0, c.work);
+    else {
+      /* no carried values yet: TFP's bootstrap_results evaluates at schedule(0) (magi_v2.py:357-364); a run that
+         continues at step0 > 0 starts from values of the previous step's temperature */
+      double bt0 = bt;
+      if (cached_lp && isnan(fixed_bt) && step0 + it > 0) bt0 = schedule((double)(step0 + it - 1), min_temp);
+      lp0 = logpost_grad(h, z, bt0, g0, c.work);
+    }
     rng_normals(seed, chain, c.iter, S, p0);
     c.H0 = -lp0 + 0.5 * dot(p0, p0, S);
     c.sum_acc = 0.0; c.n_leaf = 0; c.leaf_index = 0; c.diverged = 0;

@@ -19,6 +19,10 @@ Fixtures:
                       (oracle.init_oracle; TFP / tf_keras not installable, "parity unpinned"): Fourier prior,
                       the hyper-parameter objective and its gradient at the start, 25 Adam steps of the fit,
                       thetas_init in both layouts (1500 Adam steps, illustrative phi).
+  vignette_fit.npz    `initial_fit` of the vignette through the restatement: fitted (phi1, phi2, sigma^2) after the
+                      reference's 1000 Adam steps, thetas_init after its 10 000 (both layouts), smoothed Xhat_init.
+  vignette_chains.npz written by `python -m oracle.vignette_study --golden`: per-chain theta / sigma^2 means of the
+                      reference's sampler stack (1000 + 1000 NUTS transitions, annealing schedule) on the C oracle.
 """
 import glob
 import os
@@ -152,6 +156,25 @@ def init_kat(ref):
     np.savez_compressed(os.path.join(OUT, "init_kat.npz"), **out)
 
 
+def vignette_fit(hp=None):
+    """The whole of `initial_fit` on the vignette data through the restatement (oracle.init_oracle): 1000 Adam steps of
+    the hyper-parameter fit, 10 000 of the theta initialisation in both layouts, the smoothed start."""
+    from . import init_oracle as io
+    g = np.load(os.path.join(OUT, "seir_datasets.npz"))
+    ts, X = g["ts_obs"], g["X_obs"][0][:, 1:].copy()
+    X[X < 0.0] = 0.0
+    I, Xd = mo.discretize(ts, X, 1)
+    if hp is None:
+        hp = io.fit_kernel_hparams(I, mo.linear_interpolate(Xd))
+    out = {"phi1s": hp["phi1s"], "phi2s": hp["phi2s"], "sigma_sqs": hp["sigma_sqs"]}
+    for layout in ("reference", "transpose"):
+        fit = io.initial_fit(ts, X, 1, 80, mo.f_seir3, 3, hparams=hp, theta_layout=layout)
+        out[f"thetas_init_{layout}"] = fit["thetas_init"]
+    out["Xhat_init"] = fit["Xhat_init"]
+    out["sigma_sqs_LB"] = fit["constants"].sigma_sqs_LB
+    np.savez_compressed(os.path.join(OUT, "vignette_fit.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = reference_object()
@@ -160,6 +183,7 @@ def main():
     seir_datasets()
     logpost_kat(ref)
     init_kat(ref)
+    vignette_fit()
     for f in sorted(glob.glob(os.path.join(OUT, "*.npz"))):
         print(f, os.path.getsize(f))
 

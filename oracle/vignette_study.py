@@ -96,9 +96,17 @@ def main():
     ap.add_argument("--hparams", default=None, help="npz with phi1s/phi2s/sigma_sqs (skips the 1000-step fit)")
     ap.add_argument("--thetas-init", default=None, help="comma-separated override of thetas_init")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--golden", action="store_true",
+                    help="write tests/golden/vignette_chains.npz: the reference's settings, intended theta start, "
+                         "hyper-parameters of tests/golden/vignette_fit.npz")
     a = ap.parse_args()
     ts, X = vignette_data()
+    if a.golden:
+        a.layout, a.cached, a.fixed_bt, a.burnin, a.results, a.depth = "transpose", 1, None, 1000, 1000, 10
+        a.hparams = os.path.join(GOLDEN, "vignette_fit.npz")
     hp = dict(np.load(a.hparams)) if a.hparams else None
+    if hp is not None:
+        hp = {k: hp[k] for k in ("phi1s", "phi2s", "sigma_sqs")}
     t0 = time.time()
     fit = io.initial_fit(ts, X, 1, 80, mo.f_seir3, 3, hparams=hp, theta_layout=a.layout)
     if a.thetas_init:
@@ -118,6 +126,16 @@ def main():
     if a.out:
         with open(a.out, "w") as f:
             json.dump(out, f, indent=1)
+    if a.golden:
+        D, nb = 3, a.burnin
+        tails = np.stack([r["tail"] for r in runs])[:, nb:]
+        sp = lambda v: np.logaddexp(0.0, v)
+        np.savez_compressed(os.path.join(GOLDEN, "vignette_chains.npz"),
+                            theta_chain_means=sp(tails[:, :, D:]).mean(axis=1),
+                            log_sigma_sq_chain_means=np.log(sp(tails[:, :, :D]) + fit["constants"].sigma_sqs_LB).mean(axis=1),
+                            step_size_final=np.array([r["step_size"][-1] for r in runs]),
+                            mean_leapfrogs=np.array([r["leapfrogs"].mean() for r in runs]),
+                            settings=np.array([a.burnin, a.results, a.depth, a.cached, a.seed, a.chains]))
 
 
 if __name__ == "__main__":

@@ -1,8 +1,9 @@
 """End to end through the reference-facing class `MAGI_v2` (same constructor / initial_fit / predict as
 magi_v2.py:32, :82, :286) on the reference's own data: vignette.ipynb settings on SEIR_seed=0 (config 1)
-and the 20 alpha x seed datasets as one batch (config 2).  The statistical bar is the north_star's:
-posterior means of theta within Monte-Carlo error of each other across chains and near the truth
-(6.0, 0.6, 1.8) / the vignette's printed means (5.831, 0.565, 1.77; vignette.ipynb:281-283)."""
+and the 20 alpha x seed datasets as one batch (config 2).  The statistical bar is the north_star's: posterior means
+of theta within Monte-Carlo error -- of the oracle's chains for the same configuration (the notebook's printed means
+(5.831, 0.565, 1.77; vignette.ipynb:281-283) are not reproducible from the reference's code as it stands:
+profiles/r02_vignette.md)."""
 import numpy as np
 import pytest
 
@@ -21,38 +22,84 @@ def _seir3_data(which=0):
     return g["ts_obs"], X
 
 
-def test_vignette_config_end_to_end(cuda_device):
+def test_vignette_initial_fit_matches_the_restated_reference(cuda_device):
+    """vignette.ipynb:163-164 through `MAGI_v2.initial_fit` against the oracle's restatement of the same stages
+    (oracle/init_oracle.py -> tests/golden/vignette_fit.npz): GP hyper-parameters after the reference's 1000 Adam steps
+    (device: closed-form gradient on cov_build + Cholesky; oracle: torch autograd), thetas_init after its 10 000 Adam steps
+    in the reference's own layout (magi_v2.py:155-156 -- every component negative on this data) and in the intended one,
+    the smoothed start."""
     from magi_v2_b200 import MAGI_v2
     ts, X = _seir3_data(0)
+    f = load_golden("vignette_fit.npz")
     model = MAGI_v2(D_thetas=3, ts_obs=ts, X_obs=X, bandsize=80, f_vec="seir3")      # vignette.ipynb:163
     model.initial_fit(discretization=1)                                              # :164 (incl. GP hparam fit)
     assert model.I.shape == (161, 1) and model.C_d_invs.shape == (3, 161, 161)
-    assert np.all(model.phi1s > 0) and np.all((model.phi2s > 0.02) & (model.phi2s < 2.0))
-    assert np.all(model.thetas_init > 0)
-    res = model.predict(num_results=600, num_burnin_steps=600, n_chains=8, n_leapfrog=32, seed=3)
-    th = res["thetas_samps"]                        # [chains, num_results, 3]
-    assert th.shape == (8, 600, 3) and res["X_samps"].shape == (8, 600, 161, 3)
-    assert np.isfinite(th).all()
-    acc = res["kernel_results"]["accept_prob"]
-    assert 0.4 < acc.mean() < 0.99                  # dual averaging targets 0.75 (:366)
-    chain_means = th.mean(axis=1)                   # [8, 3]
-    mean = chain_means.mean(axis=0)
-    print("theta_init", model.thetas_init, "posterior mean", mean, "chain sd", chain_means.std(axis=0))
-    # chains agree with each other (between-chain spread small against the mean)
-    assert np.all(chain_means.std(axis=0) < 0.2 * mean)
-    # The sampler starts at the gradient-matching estimate the reference computes the same way
-    # (magi_v2.py:132-179; ~(4.4, 0.35, 1.2) here, biased low by the interpolated data) and, like the
-    # reference, samples a flattened target (beta_temp ~ 0.15) with a stiff identity-mass
-    # leapfrog, so 600 short transitions do not equilibrate theta: the bar here is the right region
-    # (within a factor 2 of the truth / the vignette's unseeded single-chain means); the exact parity of the
-    # sampler is the draw-for-draw test in test_gpu_sampler.py.
-    assert np.all((mean > 0.5 * TRUTH) & (mean < 1.5 * TRUTH)), mean
-    assert np.all((mean > 0.5 * VIGNETTE) & (mean < 1.5 * VIGNETTE)), mean
-    # inferred trajectories track the (noise-free) truth of the observed components
-    g = load_golden("seir_datasets.npz")
-    Xm = res["X_samps"].mean(axis=(0, 1))[::2]      # back on the observation grid
-    rng_ = g["X_true"][0][:, 1:].max(axis=0) - g["X_true"][0][:, 1:].min(axis=0)
-    assert np.all(np.abs(Xm - g["X_true"][0][:, 1:]).max(axis=0) < 0.4 * rng_)      # noise sd is 0.05 * range
+    print("phi1", model.phi1s, f["phi1s"], "\nphi2", model.phi2s, f["phi2s"], "\nsigma_sq", model.sigma_sqs_init,
+          f["sigma_sqs"], "\nthetas_init", model.thetas_init, f["thetas_init_reference"])
+    assert np.allclose(model.phi1s, f["phi1s"], rtol=1e-3)
+    assert np.allclose(model.phi2s, f["phi2s"], rtol=1e-3)
+    assert np.allclose(model.sigma_sqs_init, f["sigma_sqs"], rtol=1e-2)
+    assert np.allclose(model.Xhat_init, f["Xhat_init"], rtol=0, atol=1e-12)
+    # thetas_init: the reference's layout (default) and the intended one, on the un-banded matrices
+    assert np.all(model.thetas_init < 0)
+    assert np.allclose(model.thetas_init, f["thetas_init_reference"], rtol=2e-2, atol=2e-3)
+    model.THETA_INIT_LAYOUT = "transpose"
+    model._device_kernel_matrices(band=None)
+    model.Xhat_init = model.X_interp_obs.copy()
+    th = model._fit_thetas_init()
+    assert np.allclose(th, f["thetas_init_transpose"], rtol=2e-2)
+    i, j = np.indices((161, 161))
+    model._apply_band()
+    for A in (model.C_d_invs, model.m_ds, model.K_d_invs):
+        assert np.all(A[:, np.abs(i - j) > 80] == 0.0)                                # :271-274
+
+
+def test_vignette_predict_runs_the_reference_sampler_by_default(cuda_device):
+    """`predict(num_results, num_burnin_steps)` with no further arguments is NUTS + dual averaging + the annealing
+    schedule (magi_v2.py:357-371), one chain, result dictionary as :412-422."""
+    from magi_v2_b200 import MAGI_v2
+    ts, X = _seir3_data(0)
+    f = load_golden("vignette_fit.npz")
+    model = MAGI_v2(D_thetas=3, ts_obs=ts, X_obs=X, bandsize=80, f_vec="seir3")
+    model.initial_fit(discretization=1, hparams={"phi1s": f["phi1s"], "phi2s": f["phi2s"], "sigma_sqs": f["sigma_sqs"]})
+    res = model.predict(num_results=6, num_burnin_steps=10)
+    kr = res["kernel_results"]
+    assert kr["sampler"] == "nuts" and res["thetas_samps"].shape == (6, 3) and res["X_samps"].shape == (6, 161, 3)
+    assert np.isfinite(res["thetas_samps"]).all() and np.all(res["sigma_sqs_samps"] > 0)
+    assert set(res) >= {"phi1s", "phi2s", "Xhat_init", "sigma_sqs_init", "thetas_init", "I", "X_samps", "sigma_sqs_samps",
+                        "thetas_samps", "kernel_results", "sample_results", "minutes_elapsed"}
+    # the reference's start: every thetas_init component is negative here, so the chain starts at softplus(-5) (:381-382)
+    assert np.allclose(np.log(np.expm1(res["thetas_samps"][0])), -5.0, atol=0.5)
+    assert kr["leapfrogs_taken"].max() >= 1 and not np.allclose(kr["step_size"], 0.1)
+
+
+def test_vignette_posterior_means_within_monte_carlo_error_of_the_oracle(cuda_device):
+    """north_star: 'posterior means of theta within Monte Carlo standard error'.  The reference's own sampler settings
+    (1000 + 1000 NUTS transitions, step 0.1, 0.8 x burn-in adaptation, annealing schedule, max_tree_depth 10) on the
+    vignette's posterior from the intended theta start: 16 chains on the device against the chains the C oracle ran on
+    the CPU from the same start (tests/golden/vignette_chains.npz, written by `python -m oracle.vignette_study --golden`).
+    Per-chain means of theta and log sigma^2 agree within 4 combined standard errors.  (Neither side is near the
+    notebook's printed (5.83, 0.565, 1.77): see profiles/r02_vignette.md.)"""
+    import os
+    from tests.helpers import GOLDEN
+    if not os.path.exists(os.path.join(GOLDEN, "vignette_chains.npz")):
+        pytest.skip("tests/golden/vignette_chains.npz not generated")
+    from magi_v2_b200 import MAGI_v2
+    ts, X = _seir3_data(0)
+    f, gc = load_golden("vignette_fit.npz"), load_golden("vignette_chains.npz")
+    model = MAGI_v2(D_thetas=3, ts_obs=ts, X_obs=X, bandsize=80, f_vec="seir3")
+    model.THETA_INIT_LAYOUT = "transpose"
+    model.initial_fit(discretization=1, hparams={"phi1s": f["phi1s"], "phi2s": f["phi2s"], "sigma_sqs": f["sigma_sqs"]})
+    R = 16
+    res = model.predict(num_results=1000, num_burnin_steps=1000, n_chains=R, seed=5)
+    th = res["thetas_samps"].mean(axis=1)                                  # [R, 3] per-chain means
+    ls = np.log(res["sigma_sqs_samps"]).mean(axis=1)
+    for mine, ref, nm in ((th, gc["theta_chain_means"], "theta"), (ls, gc["log_sigma_sq_chain_means"], "log sigma^2")):
+        se = np.sqrt(mine.var(axis=0, ddof=1) / len(mine) + ref.var(axis=0, ddof=1) / len(ref))
+        z = (mine.mean(axis=0) - ref.mean(axis=0)) / se
+        print(nm, "device", mine.mean(axis=0), "oracle", ref.mean(axis=0), "z", z)
+        assert np.all(np.abs(z) < 4.0), (nm, z)
+    assert res["kernel_results"]["leapfrogs_taken"].mean() > 500           # the adapted step needs depth-10 trees here
 
 
 def test_twenty_datasets_as_one_batch(cuda_device):
@@ -108,7 +155,7 @@ def test_completely_unobserved_component(cuda_device):
     model.initial_fit(discretization=1, seed=0)
     assert np.isfinite(model.Xhat_init).all() and np.isfinite(model.thetas_init).all()
     assert np.all(np.isfinite(model.phi1s)) and np.all(model.phi2s > 0) and np.all(model.factor_info == 0)
-    res = model.predict(num_results=60, num_burnin_steps=60, n_chains=2, n_leapfrog=8, seed=3)
+    res = model.predict(num_results=60, num_burnin_steps=60, n_chains=2, n_leapfrog=8, seed=3, sampler="hmc")
     assert res["X_samps"].shape == (2, 60, 161, 4) and np.isfinite(res["X_samps"]).all()
     assert np.isfinite(res["thetas_samps"]).all() and np.all(res["thetas_samps"] > 0)
     assert np.all(res["sigma_sqs_samps"] > 0)

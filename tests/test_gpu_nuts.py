@@ -81,7 +81,7 @@ def test_magi_batch_front_end(cuda_device):
     X[X < 0.0] = 0.0
     mb = MagiBatch(g["ts_obs"], X, 80, "seir4", device=cuda_device).initial_fit(1, hparam_iters=200)
     assert mb.thetas_init.shape == (20, 3) and np.all(np.isfinite(mb.thetas_init))
-    res = mb.predict(num_results=200, num_burnin_steps=300, n_chains=4, n_leapfrog=16, seed=2)
+    res = mb.predict(num_results=200, num_burnin_steps=300, n_chains=4, n_leapfrog=16, seed=2, sampler="hmc")
     assert res["thetas_samps"].shape == (20, 4, 200, 3) and res["sigma_sqs_samps"].shape == (20, 4, 200, 4)
     assert np.isfinite(res["thetas_samps"]).all() and np.all(res["thetas_samps"] > 0)
     assert res["X_mean"].shape == (20, 161, 4) and np.isfinite(res["X_sd"]).all()
