@@ -5,30 +5,44 @@
 //
 // Design: a persistent grid; each CTA takes whole matrices and runs a blocked, GEMM-based FP64
 // "mini-LAPACK" on them in global memory (operands stay L2-resident: <= 13 MB per matrix at
-// n = 1281) with 64x64 shared-memory tiles:
-//   left-looking blocked Cholesky (diagonal 64x64 blocks factorised and inverted in shared memory)
+// n = 1281) with 56x56 shared-memory tiles (n = 161 -> 3 x 56 = 168, n = 1281 -> 23 x 56 = 1288):
+//   left-looking blocked Cholesky (diagonal 56x56 blocks factorised and inverted in shared memory)
 //   -> blocked triangular inverse -> A^-1 = L^-T L^-1 -> GEMMs for m and K -> same for K.
-// Everything but the 64x64 diagonal work is the CTA-level GEMM below.
+// Everything but the diagonal work is the CTA-level GEMM below, whose tile products run on the FP64 tensor
+// cores (mma.sync.m8n8k4.f64 -> DMMA): one warp per 8-row strip of the tile, seven 8x8 accumulators per warp, so a
+// k-step of 4 costs 8 shared-memory operand loads for 7 DMMAs (the 4x4 DFMA register tiles of round 1 needed 8 loads
+// per 16 DFMAs and were bound by the shared-memory pipe: 14 % of the FP64 peak).
 #include "common.cuh"
 
 namespace {
 
-constexpr int kNB = 64;        // block size = GEMM tile size
+#ifndef MAGI_FACTOR_CTAS
+#define MAGI_FACTOR_CTAS 3     // resident CTAs per SM the kernel is compiled for
+#endif
+constexpr int kNB = 56;        // block size = GEMM tile size (7 x 8)
 constexpr int kKC = 16;        // GEMM k-chunk
-constexpr int kFT = 256;       // threads per CTA
-constexpr int kLd = kNB + 1;   // padded leading dimension of shared tiles
+constexpr int kFT = 32 * (kNB / 8);   // threads per CTA: one warp per 8-row strip of a tile
+constexpr int kLd = kNB + 1;   // padded leading dimension of the diagonal-block arrays
+constexpr int kLdG = 68;       // leading dimension of the GEMM staging tiles: 2 * 68 = 8 (mod 32) words, so the 16 lanes
+                               // (g = 0..3, c = 0..3) of a half warp reading [k + c][i + g] hit 16 different bank pairs
+
+__device__ __forceinline__ void dmma_f64(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
 
 struct FactorSmem {
-  double a[kKC][kLd];
-  double b[kKC][kLd];
+  double a[kKC][kLdG];
+  double b[kKC][kLdG];
   double d[kNB][kLd];   // diagonal block
   double di[kNB][kLd];  // its inverse
   int info;
 };
 
-// C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C   (all 256 threads; C row-major with ldc).
+// C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] + beta * C   (all kFT threads; C row-major with ldc).
 // op(A)(i,k) = A[i*rsA + k*csA], op(B)(k,j) = B[k*rsB + j*csB]; one of each stride pair is 1.
-// C may alias A when N <= 64 (each 64-row strip of A is fully read before the strip is stored).
+// C may alias A when N <= kNB (each kNB-row strip of A is fully read before the strip is stored).
 // Structure flags: the operands of the big products are triangular or the result is symmetric, and the tile loop
 // skips what is known to be zero / redundant (the skipped terms are exact zeros, so the values do not change):
 //   kGemmALowerT : op(A)(i,k) = 0 for k < i   (A = L^T of a lower-triangular L)      -> k starts at the tile's m0
@@ -39,19 +53,19 @@ constexpr int kGemmALowerT = 1, kGemmALower = 2, kGemmBLower = 4, kGemmSymOut = 
 
 __device__ void cta_gemm(int M, int N, int K, double alpha, const double* A, long rsA, long csA, const double* B,
                          long rsB, long csB, double beta, double* C, long ldc, FactorSmem& sm, int flags = 0) {
-  // Thread (tx, ty) owns rows ty*4 + r and columns tx + 16*c of the 64x64 tile: the four B values of a k-step are
-  // 16 doubles apart across the half-warp (conflict-free; columns tx*4 + c were a 4-way bank conflict) and the A
-  // values are a broadcast.  The next k-chunk is fetched from global memory into registers while the current one is
-  // multiplied out of shared memory.
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  // Warp w owns rows 8w .. 8w+7 of the 56x56 tile and all seven 8-column tiles; lane 4g+c holds C[8w+g][8t+2c],
+  // C[8w+g][8t+2c+1] of tile t (the DMMA accumulator layout).  The next k-chunk is fetched from global memory into
+  // registers while the current one is multiplied out of shared memory.
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
   constexpr int kPer = kNB * kKC / kFT;  // 4 elements of each operand per thread and chunk
+  constexpr int kT = kNB / 8;            // 7 column tiles
   // element -> (k, row/col) maps of the staging loads, fastest index along the operand's unit stride
   int ak[kPer], ai[kPer], bk[kPer], bj[kPer];
 #pragma unroll
   for (int q = 0; q < kPer; ++q) {
     const int e = tid + q * kFT;
-    if (csA == 1) { ak[q] = e & (kKC - 1); ai[q] = e >> 4; } else { ai[q] = e & (kNB - 1); ak[q] = e >> 6; }
-    if (csB == 1) { bj[q] = e & (kNB - 1); bk[q] = e >> 6; } else { bk[q] = e & (kKC - 1); bj[q] = e >> 4; }
+    if (csA == 1) { ak[q] = e % kKC; ai[q] = e / kKC; } else { ai[q] = e % kNB; ak[q] = e / kNB; }
+    if (csB == 1) { bj[q] = e % kNB; bk[q] = e / kNB; } else { bk[q] = e % kKC; bj[q] = e / kKC; }
   }
   for (int m0 = 0; m0 < M; m0 += kNB) {
     for (int n0 = 0; n0 < N; n0 += kNB) {
@@ -60,11 +74,9 @@ __device__ void cta_gemm(int M, int N, int K, double alpha, const double* A, lon
       if (flags & kGemmALowerT) kbeg = max(kbeg, m0);
       if (flags & kGemmBLower) kbeg = max(kbeg, n0);
       if (flags & kGemmALower) kend = min(kend, m0 + kNB);
-      double acc[4][4];
+      double acc[kT][2];
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+      for (int t = 0; t < kT; ++t) acc[t][0] = acc[t][1] = 0.0;
       double pa[kPer], pb[kPer];
       auto fetch = [&](int k0) {
 #pragma unroll
@@ -85,31 +97,26 @@ __device__ void cta_gemm(int M, int N, int K, double alpha, const double* A, lon
         __syncthreads();
         if (k0 + kKC < kend) fetch(k0 + kKC);
 #pragma unroll
-        for (int kk = 0; kk < kKC; ++kk) {
-          double av[4], bv[4];
+        for (int kk = 0; kk < kKC; kk += 4) {
+          const double av = sm.a[kk + c][8 * warp + g];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) av[r] = sm.a[kk][ty * 4 + r];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) bv[c] = sm.b[kk][tx + 16 * c];
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
+          for (int t = 0; t < kT; ++t) dmma_f64(acc[t][0], acc[t][1], av, sm.b[kk + c][8 * t + g]);
         }
         __syncthreads();
       }
+      const int gi = m0 + 8 * warp + g;
+      if (gi < M) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int gi = m0 + ty * 4 + r;
-        if (gi >= M) continue;
+        for (int t = 0; t < kT; ++t) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int gj = n0 + tx + 16 * c;
-          if (gj >= N) continue;
-          double* p = C + gi * ldc + gj;
-          const double v = beta == 0.0 ? alpha * acc[r][c] : fma(alpha, acc[r][c], beta * *p);
-          *p = v;
-          if ((flags & kGemmSymOut) && n0 < m0) C[gj * ldc + gi] = v;
+          for (int q = 0; q < 2; ++q) {
+            const int gj = n0 + 8 * t + 2 * c + q;
+            if (gj >= N) continue;
+            double* p = C + gi * ldc + gj;
+            const double v = beta == 0.0 ? alpha * acc[t][q] : fma(alpha, acc[t][q], beta * *p);
+            *p = v;
+            if ((flags & kGemmSymOut) && n0 < m0) C[gj * ldc + gi] = v;
+          }
         }
       }
     }
@@ -119,35 +126,61 @@ __device__ void cta_gemm(int M, int N, int K, double alpha, const double* A, lon
 
 // In shared memory: Cholesky of the nb x nb block sm.d (lower), then sm.di = inverse of the factor.
 // Non-positive pivot: records (base + column + 1) in sm.info (first failure only).
+//   Factorisation: right-looking, ONE barrier per column -- the trailing update of step j divides by the pivot
+//   instead of using a scaled column (d keeps L D^(1/2) until the end), so nobody waits for a square root or for the
+//   scaling of a column; the columns are scaled in one pass afterwards.
+//   Inverse X = L^-1 by forward substitution, all columns at once: thread (c, r) owns rows i = r (mod 4) of column c and
+//   keeps their partial sums in registers; step k publishes row k of X (one barrier per step).
 __device__ void smem_potrf_trtri(FactorSmem& sm, int nb, int base) {
   const int tid = threadIdx.x;
+  static_assert(kFT == 4 * kNB, "trtri: four threads per column");
   for (int j = 0; j < nb; ++j) {
-    if (tid == 0) {
-      const double p = sm.d[j][j];
-      if (!(p > 0.0) && sm.info == 0) sm.info = base + j + 1;
-      sm.d[j][j] = sqrt(p);
-    }
-    __syncthreads();
-    const double inv = 1.0 / sm.d[j][j];
-    for (int i = j + 1 + tid; i < nb; i += kFT) sm.d[i][j] *= inv;
-    __syncthreads();
-    // trailing update of the lower triangle: d[i][k] -= d[i][j] d[k][j],  j < k <= i < nb
+    __syncthreads();   // column j (and the pivot) carry every update of the steps before
+    const double p = sm.d[j][j];
+    if (tid == 0 && !(p > 0.0) && sm.info == 0) sm.info = base + j + 1;
+    const double ip = 1.0 / p;
+    // trailing update of the lower triangle: d[i][k] -= d[i][j] d[k][j] / p,  j < k <= i < nb
     for (int i = j + 1 + (tid >> 4); i < nb; i += kFT / 16) {
-      const double dij = sm.d[i][j];
+      const double dij = sm.d[i][j] * ip;
       for (int k = j + 1 + (tid & 15); k <= i; k += 16) sm.d[i][k] = fma(-dij, sm.d[k][j], sm.d[i][k]);
     }
-    __syncthreads();
   }
-  // inverse of the lower-triangular factor, one column per thread (forward substitution)
+  __syncthreads();
+  double* rs = &sm.a[0][0];   // 1 / sqrt(pivot) per column (the staging tiles are idle here)
+  if (tid < nb) rs[tid] = 1.0 / sqrt(sm.d[tid][tid]);
+  __syncthreads();
+  for (int e = tid; e < nb * nb; e += kFT) {
+    const int i = e / nb, j = e - i * nb;
+    if (j < i) sm.d[i][j] *= rs[j];
+    else if (j == i) sm.d[i][i] = sm.d[i][i] * rs[i];   // p / sqrt(p)
+  }
   for (int e = tid; e < kNB * kNB; e += kFT) sm.di[e / kNB][e % kNB] = 0.0;
   __syncthreads();
-  if (tid < nb) {
-    const int c = tid;
-    sm.di[c][c] = 1.0 / sm.d[c][c];
-    for (int i = c + 1; i < nb; ++i) {
-      double s = 0.0;
-      for (int k = c; k < i; ++k) s = fma(sm.d[i][k], sm.di[k][c], s);
-      sm.di[i][c] = -s / sm.d[i][i];
+  // X = L^-1:  X[k][c] = (delta_kc - sum_{j<k} L[k][j] X[j][c]) / L[k][k]
+  {
+    const int c = tid >> 2, r = tid & 3;
+    constexpr int kRows = kNB / 4;   // rows per thread
+    double acc[kRows];
+#pragma unroll
+    for (int q = 0; q < kRows; ++q) acc[q] = 0.0;
+    for (int k = 0; k < nb; ++k) {
+      // publish row k of column c (its owner has the complete sum)
+      if ((k & 3) == r && c < nb && c <= k) {
+        double a = 0.0;
+#pragma unroll
+        for (int q = 0; q < kRows; ++q)
+          if (q == (k >> 2)) a = acc[q];
+        sm.di[k][c] = ((c == k ? 1.0 : 0.0) - a) * rs[k];   // 1 / L[k][k] = rs[k]
+      }
+      __syncthreads();
+      if (c < nb && c <= k) {
+        const double x = sm.di[k][c];
+#pragma unroll
+        for (int q = 0; q < kRows; ++q) {
+          const int i = 4 * q + r;
+          if (i > k && i < nb) acc[q] = fma(sm.d[i][k], x, acc[q]);
+        }
+      }
     }
   }
   __syncthreads();
@@ -193,7 +226,7 @@ __device__ void cta_chol_inverse(double* Lf, double* Linv, double* T, int n, Fac
   }
 }
 
-__global__ void __launch_bounds__(kFT, 2)
+__global__ void __launch_bounds__(kFT, MAGI_FACTOR_CTAS)
 factor_kernel(const double* __restrict__ C, const double* __restrict__ Cp, const double* __restrict__ Cpp, int nmat,
               int n, int band, double jitter, double* __restrict__ Cinv, double* __restrict__ m,
               double* __restrict__ Kinv, double* __restrict__ Kout, int32_t* __restrict__ info, double* ws) {
@@ -260,7 +293,7 @@ factor_kernel(const double* __restrict__ C, const double* __restrict__ Cp, const
 int factor_grid(int nmat) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int g = 2 * sms;
+  const int g = MAGI_FACTOR_CTAS * sms;   // CTAs of 7 warps and 69 KB of shared memory
   return nmat < g ? nmat : g;
 }
 
@@ -268,10 +301,10 @@ int factor_grid(int nmat) {
 
 extern "C" size_t magi_b200_factor_workspace_bytes(int nmat, int n) {
   if (nmat <= 0 || n <= 0) return 0;
-  // sized for the largest grid any device in the box would get (2 CTAs per SM, <= 148 SMs on B200);
+  // sized for the largest grid any device in the box would get (3 CTAs per SM, <= 148 SMs on B200);
   // the launch clamps its grid to what this many bytes can serve.
   const size_t per = (3 * (size_t)n * n + (size_t)kNB * n) * sizeof(double);
-  const int g = nmat < 296 ? nmat : 296;
+  const int g = nmat < 148 * MAGI_FACTOR_CTAS ? nmat : 148 * MAGI_FACTOR_CTAS;
   return per * g;
 }
 
