@@ -71,8 +71,8 @@ def parse_args():
     ap.add_argument("--cpu-calls-per-thread", type=int, default=1500,
                     help="reference arm: dataset evaluations (8 chains each) per thread and step")
     ap.add_argument("--cpu-autograd-evals", type=int, default=12, help="reference arm: eager-autograd evaluations per worker")
-    ap.add_argument("--e2e-chunks", type=int, default=int(os.environ.get("MAGI_E2E_CHUNKS", "8")))
-    ap.add_argument("--e2e-streams", type=int, default=int(os.environ.get("MAGI_E2E_STREAMS", "3")))
+    ap.add_argument("--e2e-chunks", type=int, default=int(os.environ.get("MAGI_E2E_CHUNKS", "16")))
+    ap.add_argument("--e2e-streams", type=int, default=int(os.environ.get("MAGI_E2E_STREAMS", "4")))
     return ap.parse_args()
 
 

@@ -90,6 +90,13 @@ typedef struct {
 MAGI_API int magi_b200_nuts_momentum(uint64_t seed, const int64_t* chain_ids, uint32_t iteration, int C, int S,
                                      double* p0, magi_stream_t stream);
 
+/* One fused step of TFP's SimpleLeapfrogIntegrator for the host-driven fixed-length HMC (magi_v2_b200/hmc_host.py:
+ * grids too large for the fused sampler kernel):  p += kick * eps[c] * g;  if drift: z += eps[c] * p.
+ * kick = 1/2 for the first and the last half step, 1 when the two half kicks of consecutive steps are applied as one.
+ * z, p, g: [C,S]; eps: [C].  Also returns, if energy != NULL, energy[c] = 1/2 |p_c|^2 after the kick (drift == 0). */
+MAGI_API int magi_b200_hmc_kick_drift(int C, int S, double* z, double* p, const double* g, const double* eps, double kick,
+                                      int drift, double* energy, magi_stream_t stream);
+
 /* `magi_b200_nuts_leaf_post` that, with next != 0, also performs the first half of the NEXT leaf's step for the chains
  * it updates (ph <- p_new + e/2 g_new; Xn, sn, tn <- z_new + e ph): then only the first leaf of a subtree needs
  * `magi_b200_nuts_leaf_pre`.  ph, Xn, sn, tn are read and written. */

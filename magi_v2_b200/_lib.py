@@ -67,6 +67,8 @@ _SIGNATURES = {
     "magi_b200_logpost_grad_wide": (C.c_int, [C.POINTER(Problem)] + [C.c_void_p] * 9 + [C.c_size_t, C.c_void_p]),
     "magi_b200_probe_fp64": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "magi_b200_nuts_momentum": (C.c_int, [C.c_uint64, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "magi_b200_hmc_kick_drift": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                           C.c_int, C.c_void_p, C.c_void_p]),
     "magi_b200_nuts_uniforms": (C.c_int, [C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "magi_b200_nuts_subtree_begin": (C.c_int, [C.POINTER(NutsSubtree), C.POINTER(NutsTree), C.c_void_p]),

@@ -17,7 +17,7 @@
 namespace {
 
 #ifndef MAGI_FACTOR_CTAS
-#define MAGI_FACTOR_CTAS 3     // resident CTAs per SM the kernel is compiled for
+#define MAGI_FACTOR_CTAS 2     // resident CTAs per SM the kernel is compiled for (3: 80 registers, spills, slower)
 #endif
 constexpr int kNB = 56;        // block size = GEMM tile size (7 x 8)
 constexpr int kKC = 16;        // GEMM k-chunk
@@ -82,9 +82,11 @@ __device__ void cta_gemm(int M, int N, int K, double alpha, const double* A, lon
 #pragma unroll
         for (int q = 0; q < kPer; ++q) {
           const int gi = m0 + ai[q], gk = k0 + ak[q];
-          pa[q] = (gi < M && gk < K) ? A[gi * rsA + gk * csA] : 0.0;
+          // (k < kend, not k < K: with 56-wide blocks a 16-deep chunk can reach past the end of a triangular
+          // operand's block, into entries that are never written)
+          pa[q] = (gi < M && gk < kend) ? A[gi * rsA + gk * csA] : 0.0;
           const int gj = n0 + bj[q], gk2 = k0 + bk[q];
-          pb[q] = (gj < N && gk2 < K) ? B[gk2 * rsB + gj * csB] : 0.0;
+          pb[q] = (gj < N && gk2 < kend) ? B[gk2 * rsB + gj * csB] : 0.0;
         }
       };
       fetch(kbeg);
@@ -138,21 +140,20 @@ __device__ void smem_potrf_trtri(FactorSmem& sm, int nb, int base) {
     __syncthreads();   // column j (and the pivot) carry every update of the steps before
     const double p = sm.d[j][j];
     if (tid == 0 && !(p > 0.0) && sm.info == 0) sm.info = base + j + 1;
-    const double ip = 1.0 / p;
     // trailing update of the lower triangle: d[i][k] -= d[i][j] d[k][j] / p,  j < k <= i < nb
     for (int i = j + 1 + (tid >> 4); i < nb; i += kFT / 16) {
-      const double dij = sm.d[i][j] * ip;
+      const double dij = sm.d[i][j] / p;
       for (int k = j + 1 + (tid & 15); k <= i; k += 16) sm.d[i][k] = fma(-dij, sm.d[k][j], sm.d[i][k]);
     }
   }
   __syncthreads();
-  double* rs = &sm.a[0][0];   // 1 / sqrt(pivot) per column (the staging tiles are idle here)
-  if (tid < nb) rs[tid] = 1.0 / sqrt(sm.d[tid][tid]);
+  double* rs = &sm.a[0][0];   // sqrt(pivot) per column (the staging tiles are idle here)
+  if (tid < nb) rs[tid] = sqrt(sm.d[tid][tid]);
   __syncthreads();
   for (int e = tid; e < nb * nb; e += kFT) {
     const int i = e / nb, j = e - i * nb;
-    if (j < i) sm.d[i][j] *= rs[j];
-    else if (j == i) sm.d[i][i] = sm.d[i][i] * rs[i];   // p / sqrt(p)
+    if (j < i) sm.d[i][j] /= rs[j];
+    else if (j == i) sm.d[i][i] = rs[i];
   }
   for (int e = tid; e < kNB * kNB; e += kFT) sm.di[e / kNB][e % kNB] = 0.0;
   __syncthreads();
@@ -170,7 +171,7 @@ __device__ void smem_potrf_trtri(FactorSmem& sm, int nb, int base) {
 #pragma unroll
         for (int q = 0; q < kRows; ++q)
           if (q == (k >> 2)) a = acc[q];
-        sm.di[k][c] = ((c == k ? 1.0 : 0.0) - a) * rs[k];   // 1 / L[k][k] = rs[k]
+        sm.di[k][c] = ((c == k ? 1.0 : 0.0) - a) / rs[k];   // L[k][k] = rs[k]
       }
       __syncthreads();
       if (c < nb && c <= k) {

@@ -348,6 +348,48 @@ extern "C" int magi_b200_nuts_momentum(uint64_t seed, const int64_t* chain_ids, 
   return magi_cuda_status(cudaGetLastError());
 }
 
+namespace {
+// one CTA per chain: p += kick eps g (, z += eps p) (, energy = 1/2 |p|^2)
+__global__ void __launch_bounds__(kThreads) hmc_kick_drift_kernel(int S, double* __restrict__ z, double* __restrict__ p,
+                                                                 const double* __restrict__ g,
+                                                                 const double* __restrict__ eps, double kick, int drift,
+                                                                 double* __restrict__ energy) {
+  const size_t c = blockIdx.x;
+  const double e = eps[c], h = kick * e;
+  double ke = 0.0;
+  for (int i = threadIdx.x; i < S; i += kThreads) {
+    const size_t o = c * S + i;
+    const double pn = fma(h, g[o], p[o]);
+    p[o] = pn;
+    if (drift) z[o] = fma(e, pn, z[o]);
+    ke = fma(pn, pn, ke);
+  }
+  if (energy) {
+    __shared__ double part[kThreads / 32];
+    ke = magi_warp_sum(ke);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ke;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < kThreads / 32; ++w) t += part[w];
+      energy[c] = 0.5 * t;
+    }
+  }
+}
+}  // namespace
+
+extern "C" int magi_b200_hmc_kick_drift(int C, int S, double* z, double* p, const double* g, const double* eps, double kick,
+                                        int drift, double* energy, magi_stream_t stream) {
+  if (C <= 0) return -1;
+  if (S <= 0) return -2;
+  if (!z && drift) return -3;
+  if (!p) return -4;
+  if (!g) return -5;
+  if (!eps) return -6;
+  hmc_kick_drift_kernel<<<C, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(S, z, p, g, eps, kick, drift, energy);
+  return magi_cuda_status(cudaGetLastError());
+}
+
 extern "C" int magi_b200_nuts_subtree_begin(const magi_nuts_subtree_t* st, const magi_nuts_tree_t* tree,
                                             magi_stream_t stream) {
   if (int s = check_subtree(st)) return s;

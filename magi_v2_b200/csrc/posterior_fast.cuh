@@ -478,10 +478,19 @@ __device__ void fast_eval(const FastScratch<M, NP>& S, TileStream<M>& ts, const 
   bool obs[D];
   {
     const size_t ob = ((size_t)b * n + (valid ? j : 0)) * D;
+    if (D == 4 && (reinterpret_cast<uintptr_t>(pb.y) & 15) == 0 && (reinterpret_cast<uintptr_t>(pb.mask) & 3) == 0) {
+      // 32 bytes of y and 4 bytes of mask per grid point
+      const double2 y01 = ldg_f64x2(pb.y + ob), y23 = ldg_f64x2(pb.y + ob + 2);
+      const unsigned mk = __ldg(reinterpret_cast<const unsigned*>(pb.mask + ob));
+      yv[0] = y01.x; yv[1] = y01.y; yv[2 % D] = y23.x; yv[3 % D] = y23.y;
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      obs[d] = valid && pb.mask[ob + d] != 0;
-      yv[d] = pb.y[ob + d];
+      for (int d = 0; d < D; ++d) obs[d] = valid && ((mk >> (8 * d)) & 0xffu) != 0;
+    } else {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        obs[d] = valid && pb.mask[ob + d] != 0;
+        yv[d] = pb.y[ob + d];
+      }
     }
   }
 #pragma unroll
@@ -581,8 +590,16 @@ __device__ void fast_load_item(const FastScratch<M, NP>& S, const magi_problem_t
       const int ch = c2 + q;
       const bool ok = ch < nr && j < n;
       const double* xp = X + ((chain0 + (ok ? ch : 0)) * n + (ok ? j : 0)) * D;
+      double xv[D];
+      if (D == 4 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {   // 32 contiguous bytes: two 128-bit loads
+        const double2 x01 = ldg_f64x2(xp), x23 = ldg_f64x2(xp + 2);
+        xv[0] = x01.x; xv[1] = x01.y; xv[2 % D] = x23.x; xv[3 % D] = x23.y;
+      } else {
 #pragma unroll
-      for (int d = 0; d < D; ++d) S.Xc()[S.vix(d, ch, j)] = ok ? xp[d] - mu[d] : 0.0;
+        for (int d = 0; d < D; ++d) xv[d] = xp[d];
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) S.Xc()[S.vix(d, ch, j)] = ok ? xv[d] - mu[d] : 0.0;
     }
   }
   if (tid < kCh * D) {

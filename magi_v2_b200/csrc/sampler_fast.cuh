@@ -51,6 +51,7 @@ logpost_grad_fast_kernel(magi_problem_t pb, const double* __restrict__ X, const 
   if (fast_kernel_prologue(S, ts, pb, 1)) return;
   for (int item = blockIdx.x; fast_item<M>(pb, item, b, nr, chain0); item += gridDim.x) {
     fast_load_item(S, pb, b, X, sig_pre, th_pre, chain0, nr);
+    MAGI_TR(21)
     {  // the next item's chain states (own elements): into L2 while this item is evaluated
       int bn, nrn;
       size_t c0n;
@@ -71,11 +72,17 @@ logpost_grad_fast_kernel(magi_problem_t pb, const double* __restrict__ X, const 
         if (c2 + q < nr) {
           const double bt = btv[c2 + q];
           double* o = gX + ((chain0 + c2 + q) * n + j) * D;
+          if (D == 4 && (reinterpret_cast<uintptr_t>(gX) & 15) == 0) {   // two 128-bit stores
+            *reinterpret_cast<double2*>(o) = make_double2(bt * gxr[0][q], bt * gxr[1][q]);
+            *reinterpret_cast<double2*>(o + 2) = make_double2(bt * gxr[2 % D][q], bt * gxr[3 % D][q]);
+          } else {
 #pragma unroll
-          for (int d = 0; d < D; ++d) o[d] = bt * gxr[d][q];
+            for (int d = 0; d < D; ++d) o[d] = bt * gxr[d][q];
+          }
         }
       }
     }
+    MAGI_TR(20)
     if (tid < nr) {
       const double bt = btv[tid];
       lp[chain0 + tid] = bt * S.L()[tid];

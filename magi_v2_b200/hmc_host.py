@@ -37,6 +37,15 @@ def hmc_run_host_(prob, X, sig_pre, th_pre, eps, da_state, *, n_iter: int, n_lea
     z = _nuts.pack_state(X, sig_pre, th_pre)
     e, da = eps.view(Cn), da_state.view(Cn, 4)
     LB = prob.LB[:, None, :]
+    ke0, ke1 = mk(Cn), mk(Cn)
+    S = z.shape[1]
+    st_ptr = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+
+    def kick(zc, pc, gc, ck, drift, energy):
+        check(lib().magi_b200_hmc_kick_drift(Cn, S, ptr(zc), ptr(pc), ptr(gc), ptr(e), float(ck), int(drift), ptr(energy),
+                                             st_ptr), "hmc_kick_drift")
+
     for it in range(n_iter):
         g_it = iter0 + it
         bt = float(fixed_beta_temp) if fixed_beta_temp > 0.0 else max(1.0 / math.log(g_it + 2.0), min_temp)
@@ -45,13 +54,17 @@ def hmc_run_host_(prob, X, sig_pre, th_pre, eps, da_state, *, n_iter: int, n_lea
         p0 = eng.momentum(seed, ids, g_it)
         u, _ = eng.uniforms(seed, ids, g_it, RNG_ACCEPT, 0, 1)
         zc, pc, gc, lpc = z.clone(), p0.clone(), g0, lp0
-        he = (0.5 * e)[:, None]
-        for _ in range(n_leapfrog):
-            pc = pc + he * gc
-            zc = zc + e[:, None] * pc
+        # TFP SimpleLeapfrogIntegrator on the device: one fused kick (+ drift) launch between evaluations -- the two half
+        # kicks of consecutive steps are one full kick -- and the kinetic energies from the same kernel
+        kick(zc, pc, gc, 0.0, False, ke0)                      # energy of the drawn momentum
+        for st in range(n_leapfrog):
+            kick(zc, pc, gc, 0.5 if st == 0 else 1.0, True, None)
             lpc, gc = eng.value_and_grad(zc)
-            pc = pc + he * gc
-        dH = (-lpc + 0.5 * (pc * pc).sum(1)) - (-lp0 + 0.5 * (p0 * p0).sum(1))
+        if n_leapfrog > 0:
+            kick(zc, pc, gc, 0.5, False, ke1)
+        else:
+            ke1.copy_(ke0)
+        dH = (-lpc + ke1) - (-lp0 + ke0)
         ap = torch.where(torch.isfinite(dH), torch.exp(torch.clamp(-dH, max=0.0)), torch.zeros_like(dH))
         accept = u[:, 0] < ap
         z.copy_(torch.where(accept[:, None], zc, z))

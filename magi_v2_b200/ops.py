@@ -238,7 +238,7 @@ class PosteriorProblem:
         return lp, gX, gsig, gth
 
     # -- (3b) with HOST buffers: what a host-side sampler (the reference's TFP loop) would call ----------
-    def host_pipeline(self, R: int, n_chunks: int = 8, n_streams: int = 3) -> "HostPipeline":
+    def host_pipeline(self, R: int, n_chunks: int = 16, n_streams: int = 4) -> "HostPipeline":
         """Pinned host staging + device mirrors for `logpost_grad` on HOST data (see HostPipeline)."""
         key = (int(R), int(n_chunks), int(n_streams))
         if self._host is None or self._host.key != key:
@@ -251,7 +251,7 @@ class PosteriorProblem:
         return mk(self.B, R), mk(self.B, R, self.n, self.D), mk(self.B, R, self.D), mk(self.B, R, self.P)
 
     def logpost_grad_host(self, X: Tensor, sig_pre: Tensor, th_pre: Tensor, beta_temp: Tensor, out=None,
-                          n_chunks: int = 8, n_streams: int = 3):
+                          n_chunks: int = 16, n_streams: int = 4):
         """`logpost_grad` for ordinary HOST tensors: copies them into the pipeline's pinned staging blocks, runs it and
         copies the results out.  Convenience form -- a caller that wants the full PCIe rate fills
         `host_pipeline(R).inputs(c)` in place and reads `.outputs(c)` (no host-side copies).  Returns host tensors

@@ -39,7 +39,7 @@ def test_host_only_entry_points():
     assert L.magi_b200_model_dims(99, ctypes.byref(D), ctypes.byref(P)) == -1
     assert L.magi_b200_packed_bytes(2, 4, 161) == 2 * 4 * 3 * 168 * 168 * 8
     assert L.magi_b200_status_string(0) == b"ok"
-    assert L.magi_b200_factor_workspace_bytes(10, 161) == 10 * (3 * 161 * 161 + 64 * 161) * 8
+    assert L.magi_b200_factor_workspace_bytes(10, 161) == 10 * (3 * 161 * 161 + 56 * 161) * 8   # 56 = block size of factor.cu
     # argument validation happens before any CUDA call
     assert L.magi_b200_cov_build(None, 0, None, None, 2.01, 1, 1, 5, 0, None, None, None, None) == -1
     assert L.magi_b200_pack_matrices(None, None, None, 1, 1, 5, None, None) == -1

@@ -1,7 +1,7 @@
 """Timeline of CTA 0 of the fast log-posterior kernel, from a -DMAGI_TRACE build of the library:
     tools/build_variant.sh tr "-DMAGI_DEV_SEIR4_ONLY -DMAGI_TRACE"
     MAGI_B200_LIB=$PWD/variants/libmagi_tr.so python tools/trace_fast.py [B]
-Tags: 10 eval begin | 11..17 after the barriers of fast_eval | per chunk: 2 wait begin, 3 data there, 4 refill issued,
+Tags: 10 eval begin | 11..17 after the barriers of fast_eval | 20 gradient stored | 21 next item loaded | per chunk: 2 wait begin, 3 data there, 4 refill issued,
 5 contracted.  Prints, per warp, where the cycles of one evaluation go."""
 import ctypes as C
 import sys
