@@ -90,6 +90,15 @@ MAGI_API int magi_b200_factor_derive(const double* C, const double* Cp, const do
                             int band, double jitter, double* Cinv, double* m, double* Kinv, double* K,
                             int32_t* info, void* workspace, size_t workspace_bytes, magi_stream_t stream);
 
+/* Inverse and log-determinant of nmat symmetric positive definite matrices of order n (the Gaussian-process
+ * covariance S = phi1 R(phi2) + (sigma^2 + jitter) I of the hyper-parameter fit, magi_v2.py:594-597, where TFP
+ * factorises inside MultivariateNormalTriL / GaussianProcess.log_prob) -- the same blocked Cholesky, triangular
+ * inverse and L^-T L^-1 product as `magi_b200_factor_derive`.
+ *   A [nmat,n,n] (lower triangle read), Ainv [nmat,n,n] (full symmetric), logdet [nmat], info [nmat] (0 ok; k > 0:
+ *   not positive definite at pivot k); workspace: magi_b200_factor_workspace_bytes(nmat, n) bytes                   */
+MAGI_API int magi_b200_spd_inverse(const double* A, int nmat, int n, double* Ainv, double* logdet, int32_t* info,
+                                   void* workspace, size_t workspace_bytes, magi_stream_t stream);
+
 /* ---- (3a) capture the constants of the log-posterior ---------------------------------------------
  * Replaces the closure capture at magi_v2.py:294-296: re-lays C^-1, m, K^-1 [B, D, n, n] into the
  * sampler's device format (opaque; per (b,d): sym(C^-1) | m | sym(K^-1), each padded with zeros to

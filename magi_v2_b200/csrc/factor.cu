@@ -291,6 +291,39 @@ factor_kernel(const double* __restrict__ C, const double* __restrict__ Cp, const
   }
 }
 
+// A -> A^-1 (full symmetric) and log det A, one matrix per CTA at a time (include/magi_b200.h: magi_b200_spd_inverse)
+__global__ void __launch_bounds__(kFT, MAGI_FACTOR_CTAS)
+spd_inverse_kernel(const double* __restrict__ A, int nmat, int n, double* __restrict__ Ainv,
+                   double* __restrict__ logdet, int32_t* __restrict__ info, double* ws) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  FactorSmem& sm = *reinterpret_cast<FactorSmem*>(smraw);
+  const int tid = threadIdx.x;
+  const size_t nn = (size_t)n * n;
+  double* Lf = ws + (size_t)blockIdx.x * (3 * nn + (size_t)kNB * n);
+  double* Linv = Lf + nn;
+  double* T = Linv + 2 * nn;
+  for (int mat = blockIdx.x; mat < nmat; mat += gridDim.x) {
+    if (tid == 0) sm.info = 0;
+    for (size_t e = tid; e < nn; e += kFT) Lf[e] = A[mat * nn + e];
+    __syncthreads();
+    cta_chol_inverse(Lf, Linv, T, n, sm);
+    // log det A = 2 sum_i log L_ii (fixed summation order: thread 0 adds the per-thread partial sums)
+    double part = 0.0;
+    for (int i = tid; i < n; i += kFT) part += log(Lf[(size_t)i * n + i]);
+    double* red = &sm.a[0][0];
+    red[tid] = part;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int k = 0; k < kFT; ++k) t += red[k];
+      logdet[mat] = 2.0 * t;
+      info[mat] = sm.info;
+    }
+    __syncthreads();
+    cta_gemm(n, n, n, 1.0, Linv, 1, n, Linv, n, 1, 0.0, Ainv + mat * nn, n, sm, kGemmALowerT | kGemmBLower | kGemmSymOut);
+  }
+}
+
 int factor_grid(int nmat) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -332,5 +365,26 @@ extern "C" int magi_b200_factor_derive(const double* C, const double* Cp, const 
   if (e != cudaSuccess) return magi_cuda_status(e);
   factor_kernel<<<grid, kFT, sizeof(FactorSmem), static_cast<cudaStream_t>(stream)>>>(
       C, Cp, Cpp, nmat, n, band, jitter, Cinv, m, Kinv, K, info, static_cast<double*>(workspace));
+  return magi_cuda_status(cudaGetLastError());
+}
+
+extern "C" int magi_b200_spd_inverse(const double* A, int nmat, int n, double* Ainv, double* logdet, int32_t* info,
+                                     void* workspace, size_t workspace_bytes, magi_stream_t stream) {
+  if (!A) return -1;
+  if (nmat <= 0) return -2;
+  if (n <= 1) return -3;
+  if (!Ainv) return -4;
+  if (!logdet) return -5;
+  if (!info) return -6;
+  static_assert(kFT <= kKC * kLdG, "the reduction buffer of spd_inverse_kernel aliases the staging tile");
+  const size_t per = (3 * (size_t)n * n + (size_t)kNB * n) * sizeof(double);
+  int grid = factor_grid(nmat);
+  if (!workspace || workspace_bytes < per) return -7;
+  if ((size_t)grid * per > workspace_bytes) grid = (int)(workspace_bytes / per);
+  cudaError_t e = cudaFuncSetAttribute(spd_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(FactorSmem));
+  if (e != cudaSuccess) return magi_cuda_status(e);
+  spd_inverse_kernel<<<grid, kFT, sizeof(FactorSmem), static_cast<cudaStream_t>(stream)>>>(
+      A, nmat, n, Ainv, logdet, info, static_cast<double*>(workspace));
   return magi_cuda_status(cudaGetLastError());
 }

@@ -9,8 +9,8 @@ maximising, per component,
 normalisation removes).  TFP autodiff is replaced by the closed-form gradient
     d ll / d h = 1/2 tr( (a a^T - S^-1) dS/dh ),   a = S^-1 (x - mu),
 with dS/dphi1 = C/phi1, dS/dsigma^2 = I and dS/dphi2 = -C'_{ij} (s_i - s_j)/phi2, where C and C' come
-from the library's Matern kernel (torch.ops.magi_b200.cov_build).  The n x n Cholesky factorisations use
-torch.linalg (library call; this stage is outside the sampling hot path)."""
+from the library's Matern kernel (torch.ops.magi_b200.cov_build) and S^-1, log det S from the library's batched
+Cholesky (`magi_b200_spd_inverse`, csrc/factor.cu); the remaining algebra is batched torch tensor code."""
 from __future__ import annotations
 
 import numpy as np
@@ -45,11 +45,10 @@ def objective_and_grad(v, grid, dt, xc, loc, scale, uniform_grid: bool = False):
     phi1, phi2, sig2 = h[0].contiguous(), h[1].contiguous(), h[2]
     C, Cp, _ = ops.cov_build(grid, phi1, phi2, NU, uniform_grid)
     S = C + (sig2 + JITTER)[..., None, None] * eye
-    L, info = torch.linalg.cholesky_ex(S)
+    Sinv, logdet, info = ops.spd_inverse(S.contiguous())     # the library's blocked Cholesky (csrc/factor.cu)
     if int(info.abs().max()) != 0:
         bad = torch.nonzero(info)[:4].tolist()
         raise np.linalg.LinAlgError(f"GP covariance not positive definite for (dataset, component) {bad}")
-    Sinv = torch.cholesky_inverse(L)
     a = (Sinv @ xc[..., None])[..., 0]                                          # [B,D,n]
     W = a[..., :, None] * a[..., None, :] - Sinv
     g_phi1 = 0.5 * (W * C).sum(dim=(-1, -2)) / phi1
@@ -58,8 +57,7 @@ def objective_and_grad(v, grid, dt, xc, loc, scale, uniform_grid: bool = False):
     g = torch.stack([g_phi1, g_phi2, g_sig2])
     g = g - (h - loc) / scale ** 2                                              # truncated-normal priors
     g = -g * torch.sigmoid(v)                                                   # loss = -log_prob; softplus chain rule
-    ll = (-0.5 * (xc * a).sum(-1) - torch.log(torch.diagonal(L, dim1=-2, dim2=-1)).sum(-1)
-          - 0.5 * n * np.log(2 * np.pi))
+    ll = -0.5 * (xc * a).sum(-1) - 0.5 * logdet - 0.5 * n * np.log(2 * np.pi)
     obj = ll - 0.5 * (((h - loc) / scale) ** 2).sum(0)
     return obj, g
 

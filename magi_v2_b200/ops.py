@@ -84,6 +84,23 @@ def factor_derive(C_: Tensor, Cp: Tensor, Cpp: Tensor, band: int, jitter: float)
     return Cinv, m, Kinv, K, info
 
 
+def spd_inverse(A: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """A [...,n,n] symmetric positive definite -> (A^-1 [...,n,n], log det A [...], info [...]) by the library's blocked
+    Cholesky (`magi_b200_spd_inverse`; info > 0: not positive definite at that pivot)."""
+    _chk(A, "A")
+    n = A.shape[-1]
+    nmat = A.numel() // (n * n)
+    with torch.cuda.device(A.device):
+        Ainv = torch.empty_like(A)
+        logdet = torch.empty(A.shape[:-2], dtype=torch.float64, device=A.device)
+        info = torch.empty(A.shape[:-2], dtype=torch.int32, device=A.device)
+        wsb = lib().magi_b200_factor_workspace_bytes(nmat, n)
+        ws = torch.empty(wsb // 8, dtype=torch.float64, device=A.device)
+        st = lib().magi_b200_spd_inverse(_ptr(A), nmat, n, _ptr(Ainv), _ptr(logdet), _ptr(info), _ptr(ws), wsb, _stream(A))
+    check(st, "spd_inverse")
+    return Ainv, logdet, info
+
+
 @factor_derive.register_fake
 def _(C_, Cp, Cpp, band, jitter):
     return (torch.empty_like(C_), torch.empty_like(C_), torch.empty_like(C_), torch.empty_like(C_),

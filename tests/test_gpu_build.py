@@ -175,3 +175,26 @@ def test_end_to_end_build_feeds_the_log_posterior(cuda_device):
         o = mo.log_posterior_and_grad_autograd(X[r], s[r], tau[r], 0.8, c)
         assert abs(float(lp[0, r]) - o[0]) <= 1e-9 * abs(o[0])
         assert relerr(gX[0, r].cpu().numpy(), o[1]) <= 1e-9
+
+
+@pytest.mark.parametrize("n,nmat", [(41, 7), (81, 5), (130, 3), (161, 4)])
+def test_spd_inverse_matches_lapack(n, nmat, cuda_device):
+    """`magi_b200_spd_inverse` (the hyper-parameter fit's S^-1 and log det S, magi_v2.py:594-597) against LAPACK on
+    the GP covariances it is used for: Matern block + noise."""
+    import torch
+    from magi_v2_b200 import ops
+    rng = np.random.default_rng(n)
+    I = np.linspace(0.0, 4.0, n)
+    A = np.stack([mo.matern_blocks(I, rng.uniform(0.01, 2.0), rng.uniform(0.2, 1.0), 2.01)[0] +
+                  rng.uniform(1e-4, 1e-2) * np.eye(n) for _ in range(nmat)])
+    Ainv, logdet, info = ops.spd_inverse(_T(A, cuda_device))
+    torch.cuda.synchronize()
+    assert int(info.abs().max()) == 0
+    for k in range(nmat):
+        ref = np.linalg.inv(A[k])
+        assert relerr(Ainv[k].cpu().numpy(), ref) <= 1e-13 * np.linalg.cond(A[k])
+        assert abs(float(logdet[k]) - np.linalg.slogdet(A[k])[1]) <= 1e-9 * n
+    bad = A.copy()
+    bad[1, 3, 3] = -1.0
+    _, _, info = ops.spd_inverse(_T(bad, cuda_device))
+    assert int(info[1]) == 4 and int(info[0]) == 0
