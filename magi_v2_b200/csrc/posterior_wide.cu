@@ -33,6 +33,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 struct Geo {
   int np, nblk, kb, rbpc, nchunk, G;  // padded n, 8-row blocks, band in blocks (<0: dense), block rows per CTA, CTAs per column of the grid, chain groups
+  int NG, GS;                         // chain groups per CTA (1 or 2: they share every matrix tile the CTA loads), CTAs per (chunk, d, b) = ceil(G / NG)
   size_t per_bg;                      // workspace doubles per (dataset, chain group)
 };
 
@@ -49,7 +50,17 @@ Geo make_geo(const magi_problem_t* pb, int sms) {
   g.nblk = g.np / 8;
   g.kb = pb->band < 0 ? -1 : (pb->band + 7) >> 3;
   g.G = (pb->R + kCh - 1) / kCh;
-  const long ctas1 = (long)g.nblk * pb->D * pb->B * g.G;       // with one block row per CTA
+  // Chain groups per CTA.  2 = every matrix tile loaded once per 16 chains instead of once per 8 -- measured SLOWER at
+  // the shape it was meant for (Lorenz-96, n = 1281, R = 64: 2.24 ms against 1.59 ms per evaluation sweep): two vector
+  // arrays are 165 KB of shared memory, i.e. one CTA of 8 warps per SM instead of two, and the register-streamed tile
+  // loads lose their latency cover.  Kept behind MAGI_WIDE_NG=2 for experiments; tests cover both.
+  g.NG = 1;
+  if (const char* f = getenv("MAGI_WIDE_NG")) {
+    if (f[0] == '2' && g.G >= 2 && (2 * (size_t)g.np * kCh + kW * 4 * 32 + 2 * kCh * pb->P) * sizeof(double) <= 200 * 1024)
+      g.NG = 2;
+  }
+  g.GS = (g.G + g.NG - 1) / g.NG;
+  const long ctas1 = (long)g.nblk * pb->D * pb->B * g.GS;      // with one block row per CTA
   long r = ctas1 / (4L * sms);
   g.rbpc = (int)(r < 1 ? 1 : (r > 8 ? 8 : r));
   g.nchunk = (g.nblk + g.rbpc - 1) / g.rbpc;
@@ -116,191 +127,238 @@ struct Args {
   for (int I = ROWW ? I0 + warp : I0; I < I1; I += ROWW ? kW : 1)
 
 // ---- pass 1: u = S_C x_c, v = m x_c, r = f - v, t1 ------------------------------------------------------------
-template <class M, bool ROWW>
+template <class M, bool ROWW, int NG>
 __global__ void __launch_bounds__(kT) wide_pass1(Args a) {
   extern __shared__ double sm[];
   constexpr int D = M::D, P = M::P;
   const Geo& g = a.g;
-  double* vs = sm;                          // [np][8]
-  double* red = vs + (size_t)g.np * kCh;    // [kW][4][32]
-  double* ths = red + kW * 4 * 32;          // [8][P]
-  // chain groups of a dataset are adjacent in launch order: they read the same matrix rows at the same time (L2 hits)
-  const int grp = blockIdx.x % g.G, chunk = blockIdx.x / g.G, d = blockIdx.y, b = blockIdx.z, bg = b * g.G + grp;
+  const size_t vsz = (size_t)g.np * kCh;
+  double* vs = sm;                          // [NG][np][8]
+  double* red = vs + NG * vsz;              // [kW][4][32]
+  double* ths = red + kW * 4 * 32;          // [NG][8][P]
+  // the chain groups of a dataset are adjacent in launch order: they read the same matrix rows at the same time (L2 hits)
+  const int grp0 = (blockIdx.x % g.GS) * NG, chunk = blockIdx.x / g.GS, d = blockIdx.y, b = blockIdx.z;
   const int n = a.pb.n, R = a.pb.R, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double mu_d = a.pb.mu[b * D + d];
-  for (int e = tid; e < g.np * kCh; e += kT) {
-    const int j = e >> 3, ch = e & 7, r = grp * kCh + ch;
-    vs[e] = (j < n && r < R) ? a.X[(((size_t)b * R + r) * n + j) * D + d] - mu_d : 0.0;
-  }
-  for (int e = tid; e < kCh * P; e += kT) {
-    const int ch = e / P, k = e % P, r = grp * kCh + ch;
-    ths[e] = r < R ? magi_softplus(a.th_pre[((size_t)b * R + r) * P + k]) : 1.0;
+#pragma unroll
+  for (int g2 = 0; g2 < NG; ++g2) {
+    for (int e = tid; e < g.np * kCh; e += kT) {
+      const int j = e >> 3, ch = e & 7, r = (grp0 + g2) * kCh + ch;
+      vs[g2 * vsz + e] = (j < n && r < R) ? a.X[(((size_t)b * R + r) * n + j) * D + d] - mu_d : 0.0;
+    }
+    for (int e = tid; e < kCh * P; e += kT) {
+      const int ch = e / P, k = e % P, r = (grp0 + g2) * kCh + ch;
+      ths[g2 * kCh * P + e] = r < R ? magi_softplus(a.th_pre[((size_t)b * R + r) * P + k]) : 1.0;
+    }
   }
   const double* matC = static_cast<const double*>(a.pb.packed) + ((size_t)(b * D + d) * 3 + 0) * g.np * g.np;
   const double* matM = matC + (size_t)g.np * g.np;
-  double* wsb = a.ws + (size_t)bg * g.per_bg;
-  double* Rr = wsb + off_R(g, D);
   __syncthreads();
   MAGI_WIDE_ROWS(I) {
     int lo, hi;
     jrange(g, I, lo, hi);
-    double c[4] = {0.0, 0.0, 0.0, 0.0};
+    double c[NG][4];
+#pragma unroll
+    for (int g2 = 0; g2 < NG; ++g2) c[g2][0] = c[g2][1] = c[g2][2] = c[g2][3] = 0.0;
 #pragma unroll 4
     for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : kW) {
       const size_t t = ((size_t)I * g.nblk + J) * 64 + (lane >> 2) * 8 + (lane & 3);
       const double a0 = matC[t], a1 = matC[t + 4], m0 = matM[t], m1 = matM[t + 4];
-      const double b0 = vs[(J * 8 + (lane & 3)) * 8 + (lane >> 2)], b1 = vs[(J * 8 + 4 + (lane & 3)) * 8 + (lane >> 2)];
-      dmma(c[0], c[1], a0, b0);
-      dmma(c[0], c[1], a1, b1);
-      dmma(c[2], c[3], m0, b0);
-      dmma(c[2], c[3], m1, b1);
+#pragma unroll
+      for (int g2 = 0; g2 < NG; ++g2) {   // the tile is loaded once for all groups of the CTA
+        const double* v = vs + g2 * vsz;
+        const double b0 = v[(J * 8 + (lane & 3)) * 8 + (lane >> 2)], b1 = v[(J * 8 + 4 + (lane & 3)) * 8 + (lane >> 2)];
+        dmma(c[g2][0], c[g2][1], a0, b0);
+        dmma(c[g2][0], c[g2][1], a1, b1);
+        dmma(c[g2][2], c[g2][3], m0, b0);
+        dmma(c[g2][2], c[g2][3], m1, b1);
+      }
     }
-    if (!ROWW) cta_reduce<4>(c, red);
-    if (ROWW || warp == 0) {
-      const int i = I * 8 + (lane >> 2);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int ch = 2 * (lane & 3) + h, r = grp * kCh + ch;
-        double rv = 0.0, t1 = 0.0;
-        if (i < n && r < R) {
-          const double* xp = a.X + (((size_t)b * R + r) * n + i) * D;
-          double x[D], fo[D];
+    for (int g2 = 0; g2 < NG; ++g2) {
+      const int grp = grp0 + g2;
+      if (!ROWW) cta_reduce<4>(c[g2], red);
+      if ((ROWW || warp == 0) && grp < g.G) {
+        double* wsb = a.ws + (size_t)(b * g.G + grp) * g.per_bg;
+        double* Rr = wsb + off_R(g, D);
+        const double* v = vs + g2 * vsz;
+        const int i = I * 8 + (lane >> 2);
 #pragma unroll
-          for (int dd = 0; dd < D; ++dd) x[dd] = xp[dd];
-          M::f(x, ths + ch * P, fo);
-          double fd = 0.0;
+        for (int h = 0; h < 2; ++h) {
+          const int ch = 2 * (lane & 3) + h, r = grp * kCh + ch;
+          double rv = 0.0, t1 = 0.0;
+          if (i < n && r < R) {
+            const double* xp = a.X + (((size_t)b * R + r) * n + i) * D;
+            double x[D], fo[D];
 #pragma unroll
-          for (int dd = 0; dd < D; ++dd) fd = dd == d ? fo[dd] : fd;
-          rv = fd - c[2 + h];
-          a.gX[(((size_t)b * R + r) * n + i) * D + d] = 2.0 * c[h];   // scratch: 2 u, finished in pass 3
-          t1 = vs[i * 8 + ch] * c[h];
+            for (int dd = 0; dd < D; ++dd) x[dd] = xp[dd];
+            M::f(x, ths + (g2 * kCh + ch) * P, fo);
+            double fd = 0.0;
+#pragma unroll
+            for (int dd = 0; dd < D; ++dd) fd = dd == d ? fo[dd] : fd;
+            rv = fd - c[g2][2 + h];
+            a.gX[(((size_t)b * R + r) * n + i) * D + d] = 2.0 * c[g2][h];   // scratch: 2 u, finished in pass 3
+            t1 = v[i * 8 + ch] * c[g2][h];
+          }
+          Rr[((size_t)d * g.np + i) * kCh + ch] = rv;
+          t1 = rows_sum(t1);
+          if (lane < 4) wsb[off_t1(g, D) + ((size_t)d * g.nblk + I) * kCh + ch] = t1;
         }
-        Rr[((size_t)d * g.np + i) * kCh + ch] = rv;
-        t1 = rows_sum(t1);
-        if (lane < 4) wsb[off_t1(g, D) + ((size_t)d * g.nblk + I) * kCh + ch] = t1;
       }
     }
   }
 }
 
 // ---- pass 2: q = S_K r, t2 ---------------------------------------------------------------------------------------
-template <bool ROWW>
+template <bool ROWW, int NG>
 __global__ void __launch_bounds__(kT) wide_pass2(Args a, int D) {
   extern __shared__ double sm[];
   const Geo& g = a.g;
-  double* vs = sm;
-  double* red = vs + (size_t)g.np * kCh;
-  const int grp = blockIdx.x % g.G, chunk = blockIdx.x / g.G, d = blockIdx.y, b = blockIdx.z, bg = b * g.G + grp;
+  const size_t vsz = (size_t)g.np * kCh;
+  double* vs = sm;                          // [NG][np][8]
+  double* red = vs + NG * vsz;
+  const int grp0 = (blockIdx.x % g.GS) * NG, chunk = blockIdx.x / g.GS, d = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double* wsb = a.ws + (size_t)bg * g.per_bg;
-  const double* Rr = wsb + off_R(g, D) + (size_t)d * g.np * kCh;
-  double* Q = wsb + off_Q(g, D) + (size_t)d * g.np * kCh;
-  for (int e = tid; e < g.np * kCh; e += kT) vs[e] = Rr[e];
+#pragma unroll
+  for (int g2 = 0; g2 < NG; ++g2) {
+    const bool live = grp0 + g2 < g.G;
+    const double* Rr = a.ws + (size_t)(b * g.G + (live ? grp0 + g2 : grp0)) * g.per_bg + off_R(g, D) + (size_t)d * vsz;
+    for (int e = tid; e < g.np * kCh; e += kT) vs[g2 * vsz + e] = live ? Rr[e] : 0.0;
+  }
   const double* matK = static_cast<const double*>(a.pb.packed) + ((size_t)(b * D + d) * 3 + 2) * g.np * g.np;
   __syncthreads();
   MAGI_WIDE_ROWS(I) {
     int lo, hi;
     jrange(g, I, lo, hi);
-    double c[2] = {0.0, 0.0};
+    double c[NG][2];
+#pragma unroll
+    for (int g2 = 0; g2 < NG; ++g2) c[g2][0] = c[g2][1] = 0.0;
 #pragma unroll 8
     for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : kW) {
       const size_t t = ((size_t)I * g.nblk + J) * 64 + (lane >> 2) * 8 + (lane & 3);
       const double a0 = matK[t], a1 = matK[t + 4];
-      dmma(c[0], c[1], a0, vs[(J * 8 + (lane & 3)) * 8 + (lane >> 2)]);
-      dmma(c[0], c[1], a1, vs[(J * 8 + 4 + (lane & 3)) * 8 + (lane >> 2)]);
-    }
-    if (!ROWW) cta_reduce<2>(c, red);
-    if (ROWW || warp == 0) {
-      const int i = I * 8 + (lane >> 2);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int ch = 2 * (lane & 3) + h;
-        Q[(size_t)i * kCh + ch] = c[h];      // rows >= n: zero tiles times zero r -> 0
-        const double t2 = rows_sum(vs[i * 8 + ch] * c[h]);
-        if (lane < 4) wsb[off_t2(g, D) + ((size_t)d * g.nblk + I) * kCh + ch] = t2;
+      for (int g2 = 0; g2 < NG; ++g2) {
+        const double* v = vs + g2 * vsz;
+        dmma(c[g2][0], c[g2][1], a0, v[(J * 8 + (lane & 3)) * 8 + (lane >> 2)]);
+        dmma(c[g2][0], c[g2][1], a1, v[(J * 8 + 4 + (lane & 3)) * 8 + (lane >> 2)]);
+      }
+    }
+#pragma unroll
+    for (int g2 = 0; g2 < NG; ++g2) {
+      const int grp = grp0 + g2;
+      if (!ROWW) cta_reduce<2>(c[g2], red);
+      if ((ROWW || warp == 0) && grp < g.G) {
+        double* wsb = a.ws + (size_t)(b * g.G + grp) * g.per_bg;
+        double* Q = wsb + off_Q(g, D) + (size_t)d * vsz;
+        const double* v = vs + g2 * vsz;
+        const int i = I * 8 + (lane >> 2);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int ch = 2 * (lane & 3) + h;
+          Q[(size_t)i * kCh + ch] = c[g2][h];      // rows >= n: zero tiles times zero r -> 0
+          const double t2 = rows_sum(v[i * 8 + ch] * c[g2][h]);
+          if (lane < 4) wsb[off_t2(g, D) + ((size_t)d * g.nblk + I) * kCh + ch] = t2;
+        }
       }
     }
   }
 }
 
 // ---- pass 3: m^T q and the point-wise assembly of dX; SSE and d/d theta partial sums -------------------------------
-template <class M, bool ROWW>
+template <class M, bool ROWW, int NG>
 __global__ void __launch_bounds__(kT) wide_pass3(Args a) {
   extern __shared__ double sm[];
   constexpr int D = M::D, P = M::P;
   const Geo& g = a.g;
-  double* vs = sm;
-  double* red = vs + (size_t)g.np * kCh;
-  double* ths = red + kW * 4 * 32;          // [8][P]
-  // chain groups of a dataset are adjacent in launch order: they read the same matrix rows at the same time (L2 hits)
-  const int grp = blockIdx.x % g.G, chunk = blockIdx.x / g.G, d = blockIdx.y, b = blockIdx.z, bg = b * g.G + grp;
+  const size_t vsz = (size_t)g.np * kCh;
+  double* vs = sm;                          // [NG][np][8]
+  double* red = vs + NG * vsz;
+  double* ths = red + kW * 4 * 32;          // [NG][8][P]
+  // the chain groups of a dataset are adjacent in launch order: they read the same matrix rows at the same time (L2 hits)
+  const int grp0 = (blockIdx.x % g.GS) * NG, chunk = blockIdx.x / g.GS, d = blockIdx.y, b = blockIdx.z;
   const int n = a.pb.n, R = a.pb.R, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double* wsb = a.ws + (size_t)bg * g.per_bg;
-  const double* Qall = wsb + off_Q(g, D);
-  for (int e = tid; e < g.np * kCh; e += kT) vs[e] = Qall[(size_t)d * g.np * kCh + e];
-  for (int e = tid; e < kCh * P; e += kT) {
-    const int ch = e / P, k = e % P, r = grp * kCh + ch;
-    ths[e] = r < R ? magi_softplus(a.th_pre[((size_t)b * R + r) * P + k]) : 1.0;
+  double bt[NG][2], isig2[NG][2];
+#pragma unroll
+  for (int g2 = 0; g2 < NG; ++g2) {
+    const bool live = grp0 + g2 < g.G;
+    const double* Qd = a.ws + (size_t)(b * g.G + (live ? grp0 + g2 : grp0)) * g.per_bg + off_Q(g, D) + (size_t)d * vsz;
+    for (int e = tid; e < g.np * kCh; e += kT) vs[g2 * vsz + e] = live ? Qd[e] : 0.0;
+    for (int e = tid; e < kCh * P; e += kT) {
+      const int ch = e / P, k = e % P, r = (grp0 + g2) * kCh + ch;
+      ths[g2 * kCh * P + e] = r < R ? magi_softplus(a.th_pre[((size_t)b * R + r) * P + k]) : 1.0;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = (grp0 + g2) * kCh + 2 * (lane & 3) + h;
+      bt[g2][h] = r < R ? a.beta_temp[(size_t)b * R + r] : 0.0;
+      isig2[g2][h] = r < R ? 1.0 / (magi_softplus(a.sig_pre[((size_t)b * R + r) * D + d]) + a.pb.LB[b * D + d]) : 0.0;
+    }
   }
   const double* matM = static_cast<const double*>(a.pb.packed) + ((size_t)(b * D + d) * 3 + 1) * g.np * g.np;
   const double inv_beta = 1.0 / a.pb.beta[b];
-  double bt[2], isig2[2];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int r = grp * kCh + 2 * (lane & 3) + h;
-    bt[h] = r < R ? a.beta_temp[(size_t)b * R + r] : 0.0;
-    isig2[h] = r < R ? 1.0 / (magi_softplus(a.sig_pre[((size_t)b * R + r) * D + d]) + a.pb.LB[b * D + d]) : 0.0;
-  }
   __syncthreads();
   MAGI_WIDE_ROWS(I) {
     int lo, hi;
     jrange(g, I, lo, hi);
-    double c[2] = {0.0, 0.0};
+    double c[NG][2];
+#pragma unroll
+    for (int g2 = 0; g2 < NG; ++g2) c[g2][0] = c[g2][1] = 0.0;
 #pragma unroll 8
     for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : kW) {
       // (m^T)(I, J) = tile (J, I) transposed: A[row][k] = tile[k][row]
       const size_t t = ((size_t)J * g.nblk + I) * 64 + (lane & 3) * 8 + (lane >> 2);
       const double a0 = matM[t], a1 = matM[t + 32];
-      dmma(c[0], c[1], a0, vs[(J * 8 + (lane & 3)) * 8 + (lane >> 2)]);
-      dmma(c[0], c[1], a1, vs[(J * 8 + 4 + (lane & 3)) * 8 + (lane >> 2)]);
+#pragma unroll
+      for (int g2 = 0; g2 < NG; ++g2) {
+        const double* v = vs + g2 * vsz;
+        dmma(c[g2][0], c[g2][1], a0, v[(J * 8 + (lane & 3)) * 8 + (lane >> 2)]);
+        dmma(c[g2][0], c[g2][1], a1, v[(J * 8 + 4 + (lane & 3)) * 8 + (lane >> 2)]);
+      }
     }
-    if (!ROWW) cta_reduce<2>(c, red);
-    if (ROWW || warp == 0) {
-      const int i = I * 8 + (lane >> 2);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int ch = 2 * (lane & 3) + h, r = grp * kCh + ch;
-        double sse = 0.0, vth[P];
+    for (int g2 = 0; g2 < NG; ++g2) {
+      const int grp = grp0 + g2;
+      if (!ROWW) cta_reduce<2>(c[g2], red);
+      if ((ROWW || warp == 0) && grp < g.G) {
+        double* wsb = a.ws + (size_t)(b * g.G + grp) * g.per_bg;
+        const double* Qall = wsb + off_Q(g, D);
+        const int i = I * 8 + (lane >> 2);
 #pragma unroll
-        for (int k = 0; k < P; ++k) vth[k] = 0.0;
-        if (i < n && r < R) {
-          const size_t xo = (((size_t)b * R + r) * n + i) * D;
-          double x[D], gq[D], vx[D];
+        for (int h = 0; h < 2; ++h) {
+          const int ch = 2 * (lane & 3) + h, r = grp * kCh + ch;
+          double sse = 0.0, vth[P];
 #pragma unroll
-          for (int dd = 0; dd < D; ++dd) {
-            x[dd] = a.X[xo + dd];
-            gq[dd] = 2.0 * Qall[((size_t)dd * g.np + i) * kCh + ch];
+          for (int k = 0; k < P; ++k) vth[k] = 0.0;
+          if (i < n && r < R) {
+            const size_t xo = (((size_t)b * R + r) * n + i) * D;
+            double x[D], gq[D], vx[D];
+#pragma unroll
+            for (int dd = 0; dd < D; ++dd) {
+              x[dd] = a.X[xo + dd];
+              gq[dd] = 2.0 * Qall[((size_t)dd * g.np + i) * kCh + ch];
+            }
+            M::vjp(x, ths + (g2 * kCh + ch) * P, gq, vx, vth);
+            double xd = 0.0, vxd = 0.0;
+#pragma unroll
+            for (int dd = 0; dd < D; ++dd) {
+              xd = dd == d ? x[dd] : xd;
+              vxd = dd == d ? vx[dd] : vxd;
+            }
+            const double prior = a.gX[xo + d] + vxd - 2.0 * c[g2][h];
+            const size_t yo = ((size_t)b * n + i) * D + d;
+            const double e = a.pb.mask[yo] ? xd - a.pb.y[yo] : 0.0;
+            a.gX[xo + d] = bt[g2][h] * -0.5 * (prior * inv_beta + 2.0 * e * isig2[g2][h]);
+            sse = e * e;
           }
-          M::vjp(x, ths + ch * P, gq, vx, vth);
-          double xd = 0.0, vxd = 0.0;
+          sse = rows_sum(sse);
+          if (lane < 4) wsb[off_sse(g, D) + ((size_t)d * g.nblk + I) * kCh + ch] = sse;
+          if (d == 0) {
 #pragma unroll
-          for (int dd = 0; dd < D; ++dd) {
-            xd = dd == d ? x[dd] : xd;
-            vxd = dd == d ? vx[dd] : vxd;
-          }
-          const double prior = a.gX[xo + d] + vxd - 2.0 * c[h];
-          const size_t yo = ((size_t)b * n + i) * D + d;
-          const double e = a.pb.mask[yo] ? xd - a.pb.y[yo] : 0.0;
-          a.gX[xo + d] = bt[h] * -0.5 * (prior * inv_beta + 2.0 * e * isig2[h]);
-          sse = e * e;
-        }
-        sse = rows_sum(sse);
-        if (lane < 4) wsb[off_sse(g, D) + ((size_t)d * g.nblk + I) * kCh + ch] = sse;
-        if (d == 0) {
-#pragma unroll
-          for (int k = 0; k < P; ++k) {
-            const double tk = rows_sum(vth[k]);
-            if (lane < 4) wsb[off_th(g, D) + ((size_t)I * P + k) * kCh + ch] = tk;
+            for (int k = 0; k < P; ++k) {
+              const double tk = rows_sum(vth[k]);
+              if (lane < 4) wsb[off_th(g, D) + ((size_t)I * P + k) * kCh + ch] = tk;
+            }
           }
         }
       }
@@ -353,20 +411,20 @@ int sm_count() {
   return sms;
 }
 
-template <class M, bool ROWW>
+template <class M, bool ROWW, int NG>
 int launch_wide_t(const Args& a, cudaStream_t st) {
   const Geo& g = a.g;
-  const dim3 grid(g.nchunk * g.G, M::D, a.pb.B);
+  const dim3 grid(g.nchunk * g.GS, M::D, a.pb.B);
   if (grid.z > 65535) return MAGI_ERR_UNSUPPORTED;
-  const size_t smem = ((size_t)g.np * kCh + kW * 4 * 32 + kCh * M::P) * sizeof(double);
+  const size_t smem = (NG * (size_t)g.np * kCh + kW * 4 * 32 + NG * kCh * M::P) * sizeof(double);
   if (smem > 200 * 1024) return MAGI_ERR_UNSUPPORTED;
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(wide_pass1<M, ROWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
-  if ((e = cudaFuncSetAttribute(wide_pass2<ROWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
-  if ((e = cudaFuncSetAttribute(wide_pass3<M, ROWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
-  wide_pass1<M, ROWW><<<grid, kT, smem, st>>>(a);
-  wide_pass2<ROWW><<<grid, kT, smem, st>>>(a, M::D);
-  wide_pass3<M, ROWW><<<grid, kT, smem, st>>>(a);
+  if ((e = cudaFuncSetAttribute(wide_pass1<M, ROWW, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
+  if ((e = cudaFuncSetAttribute(wide_pass2<ROWW, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
+  if ((e = cudaFuncSetAttribute(wide_pass3<M, ROWW, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
+  wide_pass1<M, ROWW, NG><<<grid, kT, smem, st>>>(a);
+  wide_pass2<ROWW, NG><<<grid, kT, smem, st>>>(a, M::D);
+  wide_pass3<M, ROWW, NG><<<grid, kT, smem, st>>>(a);
   wide_final<<<a.pb.B * g.G, kT, 0, st>>>(a, M::D, M::P);
   return magi_cuda_status(cudaGetLastError());
 }
@@ -375,7 +433,8 @@ template <class M>
 int launch_wide(const Args& a, cudaStream_t st) {
   const char* force = getenv("MAGI_WIDE_ROWW");   // experiment knob: 0 / 1 overrides the choice of work split
   const bool roww = force ? (force[0] == '1' && a.g.rbpc <= kW) : a.g.rbpc == kW;
-  return roww ? launch_wide_t<M, true>(a, st) : launch_wide_t<M, false>(a, st);
+  if (a.g.NG == 2) return roww ? launch_wide_t<M, true, 2>(a, st) : launch_wide_t<M, false, 2>(a, st);
+  return roww ? launch_wide_t<M, true, 1>(a, st) : launch_wide_t<M, false, 1>(a, st);
 }
 
 int model_dims(int id, int& D, int& P) {

@@ -24,7 +24,7 @@ def _run(prob, X, s, tau, bt, device, path="cta"):
 
 @pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("model", ["seir3", "seir4", "sirw", "lorenz96"])
-@pytest.mark.parametrize("R", [1, 8, 11])
+@pytest.mark.parametrize("R", [1, 8, 11, 20])
 def test_small_batches_match_oracle(model, R, path, cuda_device):
     B = 3
     rng = np.random.default_rng(10 + R)
@@ -220,3 +220,21 @@ def test_wide_path_row_per_warp_split_matches_cta_path(cuda_device):
     o = mo.log_posterior_and_grad_autograd(X[0, r], s[0, r], tau[0, r], bt[0, r], oc)
     assert abs(res["wide"][0][0, r] - o[0]) <= TOL * abs(o[0]) and relerr(res["wide"][1][0, r], o[1]) <= TOL
     assert relerr(res["wide"][3][0, r], o[3]) <= TOL and relerr(res["wide"][2][0, r], o[2]) <= TOL
+
+
+def test_wide_path_two_chain_groups_per_cta(cuda_device, monkeypatch):
+    """The experimental MAGI_WIDE_NG=2 split of the wide path (two chain groups share every loaded matrix tile;
+    slower at n = 1281, see posterior_wide.cu) returns what the default split returns, odd group counts included."""
+    import torch
+    from magi_v2_b200 import synth
+    rng = np.random.default_rng(3)
+    prob, info, state, _ = synth.sweep_problem(3, 20, cuda_device, seed0=5, model="seir4", bandsize=80)
+    args = [torch.as_tensor(np.ascontiguousarray(state[k]), dtype=torch.float64, device=cuda_device)
+            for k in ("X", "sig_pre", "th_pre")]
+    bt = torch.as_tensor(rng.uniform(0.2, 1.0, (3, 20)), dtype=torch.float64, device=cuda_device)
+    ref = [t.clone() for t in prob.logpost_grad(*args, bt, path="wide")]
+    monkeypatch.setenv("MAGI_WIDE_NG", "2")
+    got = prob.logpost_grad(*args, bt, path="wide")
+    torch.cuda.synchronize()
+    for a, b in zip(got, ref):
+        assert torch.allclose(a, b, rtol=1e-12, atol=0.0)
