@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MAGI_B200_ABI_VERSION 2
+#define MAGI_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define MAGI_API __attribute__((visibility("default")))
@@ -102,7 +102,8 @@ MAGI_API int magi_b200_spd_inverse(const double* A, int nmat, int n, double* Ain
 /* ---- (3a) capture the constants of the log-posterior ---------------------------------------------
  * Replaces the closure capture at magi_v2.py:294-296: re-lays C^-1, m, K^-1 [B, D, n, n] into the
  * sampler's device format (opaque; per (b,d): sym(C^-1) | m | sym(K^-1), each padded with zeros to
- * np = 8*ceil(n/8) and stored as 8x8 tiles so that a warp streams 8 matrix rows as one contiguous
+ * np = 8*ceil(n/8) and stored as 8x8 tiles (element order inside a tile: the bank-conflict-free swizzle of
+ * csrc/common.cuh, ABI version 3) so that a warp streams 8 matrix rows as one contiguous
  * run; sym(A) = (A + A^T)/2 so that value AND gradient of x^T A x are those of the possibly
  * non-symmetric A the reference holds).  Done once per fit; `packed` needs
  * magi_b200_packed_bytes(B, D, n) bytes.                                                           */

@@ -9,7 +9,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MAGI_B200_LIB", os.path.join(HERE, "libmagi_b200.so"))   # override: kernel experiments
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MODEL_IDS = {"seir3": 0, "seir4": 1, "sirw": 2, "lorenz96": 3}
 COV_UNIFORM_GRID = 1
 

@@ -141,7 +141,8 @@ constexpr int kFwd = 0, kTr = 1, kNone = -1;
 // same coalesced load and transposes the fragment in registers (transpose_frag) when it is consumed.
 template <int TR>
 __device__ __forceinline__ const double* stream_ptr(const double* A, int np, int blk, int lane) {
-  return TR == kTr ? A + (size_t)blk * 64 + 2 * lane : A + (size_t)blk * (np >> 3) * 64 + 2 * lane;
+  const int lo = 2 * magi_tile_slot(lane >> 2, lane & 3);   // this lane's pair (g, c) inside a tile (common.cuh)
+  return TR == kTr ? A + (size_t)blk * 64 + lo : A + (size_t)blk * (np >> 3) * 64 + lo;
 }
 
 // Lane 4g+c holds (T[g][2c], T[g][2c+1]) of an 8x8 tile; returns (T[2c][g], T[2c+1][g]) -- the A fragments

@@ -77,7 +77,7 @@ template <class M, int NP>
 struct FastScratch {
   static constexpr int NRED = 2 + M::D + M::P;            // t1, t2, SSE_d, sum_j vth_k
   static constexpr int kCtl = 10 + 2 * M::P + 2 * M::D;   // control rows of the HMC kernel (sampler_fast.cuh)
-  static constexpr int kSmall = kCh * (5 * M::P + 5 * M::D + 1 + kCtl) + 3 * M::D;
+  static constexpr int kSmall = kCh * (5 * M::P + 6 * M::D + 1 + kCtl) + 3 * M::D;
   static_assert(NRED <= 16, "per-warp partial sums alias Wa|Wb: needs NRED <= 16");
   double* base;
   int n, np_rt;
@@ -106,6 +106,7 @@ struct FastScratch {
   __device__ __forceinline__ double* Nd() const { return mu() + M::D; }
   __device__ __forceinline__ double* LB() const { return mu() + 2 * M::D; }
   __device__ __forceinline__ double* ctl() const { return mu() + 3 * M::D; }           // [kCtl][8]
+  __device__ __forceinline__ double* isig2() const { return ctl() + kCtl * kCh; }      // [D][8] 1 / sigma^2
 
   // doubles of everything but the rings
   __host__ __device__ static size_t fixed_elems(int np_) {
@@ -299,11 +300,11 @@ __device__ void ts_producer(const FastScratch<M, NP>& S, const magi_problem_t& p
 }
 
 // One matrix pass of this warp (the next one of the stream): y = A x over the warp's tile steps, CT = kFwd for a
-// block row, kTr for a block column (tile fragment transposed in registers when it is consumed); SUB: the vector is
-// x - xsub.  Result: c0, c1 = y[chain 2c], y[chain 2c+1] at block element g (lane = 4g + c).
-// (Measured alternatives, profiles/r02_headline.md: transposing all fragments of a chunk before the slot is released,
-// and contracting a transposed pass with the tile as the B operand -- two 8-byte loads per tile, no shuffles, one
-// transpose of the result per pass -- were 8 % slower each.)
+// block row, kTr for a block column (the transposed fragment is read directly: the swizzled tile layout of common.cuh
+// makes both fragment shapes conflict-free); SUB: the vector is x - xsub.
+// Result: c0, c1 = y[chain 2c], y[chain 2c+1] at block element g (lane = 4g + c).
+// (Measured before the swizzle, profiles/r02_headline.md: transposing in registers with six shuffles per tile, lazily or
+// for a whole chunk; contracting a transposed pass with the tile as the B operand.)
 template <class M, int NP, bool SUB, int CT>
 __device__ __forceinline__ void staged_pass(const FastScratch<M, NP>& S, TileStream<M>& ts, const double* x,
                                             const double* xsub, double& c0, double& c1) {
@@ -311,6 +312,11 @@ __device__ __forceinline__ void staged_pass(const FastScratch<M, NP>& S, TileStr
   const size_t bo = (size_t)(lane >> 2) * ns + 2 * (lane & 3) + 8 * ts.lo;
   const double* bp = x + bo;
   const double* bs = SUB ? xsub + bo : nullptr;
+  // byte offsets of this lane's fragment inside a (swizzled, common.cuh) tile: forward = the pair (g, c); transposed =
+  // the elements (2c, g) and (2c+1, g), i.e. exactly the fragment of the transposed tile -- no shuffles
+  const int fg = lane >> 2, fc = lane & 3;
+  const uint32_t ofw = 16 * magi_tile_slot(fg, fc);
+  const uint32_t otr0 = 8 * magi_tile_pos(2 * fc, fg), otr1 = 8 * magi_tile_pos(2 * fc + 1, fg);
   double acc[2][2];  // two independent accumulator pairs (even / odd k-group of a step)
 #pragma unroll
   for (int q = 0; q < 2; ++q) acc[q][0] = acc[q][1] = 0.0;
@@ -323,13 +329,16 @@ __device__ __forceinline__ void staged_pass(const FastScratch<M, NP>& S, TileStr
     mbar_wait(ts.bars + 8 * slot, (ts.k / kTsSlots) & 1);
 #endif
     MAGI_TR(3)
-    const uint32_t ap = ts.ring + slot * (uint32_t)(ts.cw * 512) + 16 * lane;
+    const uint32_t ap = ts.ring + slot * (uint32_t)(ts.cw * 512);
     // The chunk's matrix fragments go to registers first and the slot is handed back to the producer AT ONCE (the
     // refill is in flight while this chunk is contracted).  All kTsMaxC loads are unconditional: beyond the chunk's
     // last tile they read other, finite ring contents that are never used.
     double2 a[kTsMaxC];
 #pragma unroll
-    for (int i = 0; i < kTsMaxC; ++i) a[i] = lds_f64x2(ap + i * 512);
+    for (int i = 0; i < kTsMaxC; ++i) {
+      if (CT == kTr) a[i] = make_double2(lds_f64(ap + i * 512 + otr0), lds_f64(ap + i * 512 + otr1));
+      else a[i] = lds_f64x2(ap + i * 512 + ofw);
+    }
     __syncwarp();   // every lane has read the slot
     ++ts.k;
     if (lane == 0) mbar_arrive(ts.bars + 8 * (kTsSlots + slot));
@@ -338,7 +347,7 @@ __device__ __forceinline__ void staged_pass(const FastScratch<M, NP>& S, TileStr
     // to tile 0): no predicates, no loop counters, every offset an immediate
 #define MAGI_TILE(i)                                                            \
   {                                                                             \
-    const double2 av = CT == kTr ? transpose_frag(a[i]) : a[i];                 \
+    const double2 av = a[i];                                                    \
     double2 b = *reinterpret_cast<const double2*>(bp + 8 * (i));                \
     if (SUB) {                                                                  \
       const double2 b2 = *reinterpret_cast<const double2*>(bs + 8 * (i));       \
@@ -395,7 +404,9 @@ __device__ void fast_eval(const FastScratch<M, NP>& S, TileStream<M>& ts, const 
     } else {
       const int d = q - P;
       const double z = S.s()[d * kCh + c];
-      S.sig2()[d * kCh + c] = magi_softplus(z) + S.LB()[d];
+      const double s2 = magi_softplus(z) + S.LB()[d];
+      S.sig2()[d * kCh + c] = s2;
+      S.isig2()[d * kCh + c] = 1.0 / s2;
       S.sgs()[d * kCh + c] = magi_sigmoid(z);
     }
   }
@@ -414,7 +425,7 @@ __device__ void fast_eval(const FastScratch<M, NP>& S, TileStream<M>& ts, const 
 #pragma unroll
     for (int d = 0; d < D; ++d) S.FG()[S.vix(d, c2 + q, j)] = valid ? f[d] : 0.0;
   }
-  named_sync(32 * S.nblk());
+  // (no barrier: the first pass below reads Xc, which is complete, and writes Wa; f is first read by the second pass)
   MAGI_TR(12)
 
   double t1[2] = {0.0, 0.0}, t2[2] = {0.0, 0.0};
@@ -511,7 +522,7 @@ __device__ void fast_eval(const FastScratch<M, NP>& S, TileStream<M>& ts, const 
     for (int d = 0; d < D; ++d) {
       const double e = obs[d] ? x[d] - yv[d] : 0.0;
       red[2 + d] = e * e;
-      gxr[d][q] = -0.5 * ((gxr[d][q] + vx[d]) * inv_beta + 2.0 * e / S.sig2()[d * kCh + ch]);
+      gxr[d][q] = -0.5 * ((gxr[d][q] + vx[d]) * inv_beta + 2.0 * e * S.isig2()[d * kCh + ch]);
     }
 #pragma unroll
     for (int k = 0; k < P; ++k) red[2 + D + k] = valid ? vth[k] : 0.0;
@@ -560,6 +571,8 @@ __device__ void fast_eval(const FastScratch<M, NP>& S, TileStream<M>& ts, const 
     lc += magi_shfl_xor(lc, 1);
     if (q == 0) S.L()[c] = lc;
   }
+  // (a barrier of the four warps of this stage alone -- everybody else going straight on to the gradient stores or the
+  // kick of X -- was measured: no gain, profiles/r02_headline.md)
   named_sync(32 * S.nblk());
   MAGI_TR(17)
 }

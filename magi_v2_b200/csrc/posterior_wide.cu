@@ -162,8 +162,9 @@ __global__ void __launch_bounds__(kT) wide_pass1(Args a) {
     for (int g2 = 0; g2 < NG; ++g2) c[g2][0] = c[g2][1] = c[g2][2] = c[g2][3] = 0.0;
 #pragma unroll 4
     for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : kW) {
-      const size_t t = ((size_t)I * g.nblk + J) * 64 + (lane >> 2) * 8 + (lane & 3);
-      const double a0 = matC[t], a1 = matC[t + 4], m0 = matM[t], m1 = matM[t + 4];
+      const size_t t = ((size_t)I * g.nblk + J) * 64;
+      const int e0 = magi_tile_pos(lane >> 2, lane & 3), e1 = magi_tile_pos(lane >> 2, 4 + (lane & 3));
+      const double a0 = matC[t + e0], a1 = matC[t + e1], m0 = matM[t + e0], m1 = matM[t + e1];
 #pragma unroll
       for (int g2 = 0; g2 < NG; ++g2) {   // the tile is loaded once for all groups of the CTA
         const double* v = vs + g2 * vsz;
@@ -235,8 +236,8 @@ __global__ void __launch_bounds__(kT) wide_pass2(Args a, int D) {
     for (int g2 = 0; g2 < NG; ++g2) c[g2][0] = c[g2][1] = 0.0;
 #pragma unroll 8
     for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : kW) {
-      const size_t t = ((size_t)I * g.nblk + J) * 64 + (lane >> 2) * 8 + (lane & 3);
-      const double a0 = matK[t], a1 = matK[t + 4];
+      const size_t t = ((size_t)I * g.nblk + J) * 64;
+      const double a0 = matK[t + magi_tile_pos(lane >> 2, lane & 3)], a1 = matK[t + magi_tile_pos(lane >> 2, 4 + (lane & 3))];
 #pragma unroll
       for (int g2 = 0; g2 < NG; ++g2) {
         const double* v = vs + g2 * vsz;
@@ -307,8 +308,8 @@ __global__ void __launch_bounds__(kT) wide_pass3(Args a) {
 #pragma unroll 8
     for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : kW) {
       // (m^T)(I, J) = tile (J, I) transposed: A[row][k] = tile[k][row]
-      const size_t t = ((size_t)J * g.nblk + I) * 64 + (lane & 3) * 8 + (lane >> 2);
-      const double a0 = matM[t], a1 = matM[t + 32];
+      const size_t t = ((size_t)J * g.nblk + I) * 64;
+      const double a0 = matM[t + magi_tile_pos(lane & 3, lane >> 2)], a1 = matM[t + magi_tile_pos(4 + (lane & 3), lane >> 2)];
 #pragma unroll
       for (int g2 = 0; g2 < NG; ++g2) {
         const double* v = vs + g2 * vsz;

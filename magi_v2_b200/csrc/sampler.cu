@@ -28,7 +28,7 @@ __global__ void pack_kernel(const double* __restrict__ Cinv, const double* __res
       mv = mm[(size_t)i * n + j];
       sk = 0.5 * (k[(size_t)i * n + j] + k[(size_t)j * n + i]);
     }
-    const size_t t = ((size_t)(i >> 3) * nblk + (j >> 3)) * 64 + (i & 7) * 8 + (j & 7);  // tiled offset
+    const size_t t = ((size_t)(i >> 3) * nblk + (j >> 3)) * 64 + magi_tile_pos(i & 7, j & 7);  // tiled, swizzled (common.cuh)
     o[t] = sc;
     o[(size_t)np * np + t] = mv;
     o[2 * (size_t)np * np + t] = sk;

@@ -54,6 +54,9 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void named_sync(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void named_sync_n(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // bring a line into L2 and keep it there preferentially (it is read once more soon, by this or the next item)
 __device__ __forceinline__ void l2_prefetch_keep(const void* p) {
   asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));

@@ -297,8 +297,11 @@ def build_library(ts: TracedSystem, verbose: bool = False) -> str:
     so = os.path.join(d, "libmagi_user.so")
     hdr = os.path.join(d, "user_model.cuh")
     code = emit_cuda(ts)
-    if os.path.exists(so) and os.path.exists(hdr) and open(hdr).read() == code:
-        return so
+    deps = [os.path.join(HERE, "csrc", f) for f in ("posterior_wide.cu", "common.cuh", "ode_models.cuh")] + \
+           [os.path.join(os.path.dirname(HERE), "include", f) for f in ("magi_b200.h", "magi_b200_wide.h")]
+    newest = max(os.path.getmtime(f) for f in deps if os.path.exists(f))
+    if os.path.exists(so) and os.path.exists(hdr) and open(hdr).read() == code and os.path.getmtime(so) >= newest:
+        return so      # (a library older than the sources it was compiled from -- e.g. a changed packed layout -- is rebuilt)
     os.makedirs(d, exist_ok=True)
     with open(hdr, "w") as f:
         f.write(code)

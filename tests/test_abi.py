@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for nm in names:
         assert hasattr(L, nm), nm
-    assert _lib.lib().magi_b200_abi_version() == _lib.ABI_VERSION == 2
+    assert _lib.lib().magi_b200_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_host_only_entry_points():
