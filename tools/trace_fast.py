@@ -51,3 +51,15 @@ for w in (0, 5, 10, 15, 20):
             if gg[i] in (2, 3, 4, 5):
                 line.append(f"{gg[i]}:{tt[i] - tt[i - 1]}")
         print("   chunk events (tag:delta):", " ".join(line[:160]))
+
+# idle cycles of every warp before each barrier of the evaluation is released (release time - the warp's last event)
+print("idle before barrier release (rows: warp, columns: barriers of the third evaluation in order)")
+for w in range(NW):
+    e = ev[w, :cnt[w]]
+    t, tag = (e >> np.uint64(8)).astype(np.int64), (e & np.uint64(255)).astype(int)
+    starts = np.flatnonzero(tag == 10)
+    if len(starts) < 4:
+        continue
+    a, b = starts[2], starts[3]
+    idle = [int(t[i] - t[i - 1]) for i in range(a + 1, b + 1) if 11 <= tag[i] <= 17]
+    print(f"  warp {w:2d}: " + " ".join(f"{v:6d}" for v in idle))
