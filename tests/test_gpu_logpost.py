@@ -238,3 +238,28 @@ def test_wide_path_two_chain_groups_per_cta(cuda_device, monkeypatch):
     torch.cuda.synchronize()
     for a, b in zip(got, ref):
         assert torch.allclose(a, b, rtol=1e-12, atol=0.0)
+
+
+@pytest.mark.parametrize("N,disc,band", [(5, 1, 1), (5, 1, None), (9, 1, 2), (11, 2, 7), (12, 3, 16), (21, 3, 40),
+                                         (21, 3, 9), (21, 3, None)])
+def test_fast_path_edge_shapes(N, disc, band, cuda_device):
+    """Grid sizes and bandwidths around the edges of the TMA-staged fast path (n = 9 ... 168 = its limit; one to 21
+    block rows; bands of one tile, of every tile, not a multiple of 8; chain counts that leave a group partly empty):
+    rings of one chunk per pass, rows shorter than a chunk, a last block row that is all padding but one point."""
+    model, R, B = "seir4", 11, 2
+    rng = np.random.default_rng(N * 100 + disc)
+    consts = [synth_constants(model, seed=7 + b, N=N, disc=disc, band=band, T=2.0) for b in range(B)]
+    n = consts[0].I.shape[0]
+    assert n <= 168
+    prob = device_problem(consts, model, cuda_device)
+    st = [random_state(c, model, rng, R) for c in consts]
+    X = np.stack([a[0] for a in st]); s = np.stack([a[1] for a in st]); tau = np.stack([a[2] for a in st])
+    bt = rng.uniform(0.1, 1.5, (B, R))
+    lp, gX, gs, gt = _run(prob, X, s, tau, bt, cuda_device, "cta")
+    for b in range(B):
+        for r in (0, 7, 8, 10):
+            o = mo.log_posterior_and_grad_autograd(X[b, r], s[b, r], tau[b, r], bt[b, r], consts[b])
+            assert abs(lp[b, r] - o[0]) <= TOL * abs(o[0])
+            assert relerr(gX[b, r], o[1]) <= TOL
+            assert relerr(gs[b, r], o[2]) <= TOL
+            assert relerr(gt[b, r], o[3]) <= TOL
