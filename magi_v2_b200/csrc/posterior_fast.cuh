@@ -252,6 +252,9 @@ __device__ void ts_producer(const FastScratch<M, NP>& S, const magi_problem_t& p
   const ptrdiff_t fwd = ((ptrdiff_t)w * nblk + lo) * 64, tr = ((ptrdiff_t)lo * nblk + w) * 64;
   int item = blockIdx.x, pev = evals_per_item, ppass = 0, pleft = len;
   uint32_t kp = 0;   // chunks issued
+  // L2 eviction priorities of the copies (measured: 1.94 -> 1.86 ms): the tiles of m are read again two passes later
+  // and should still be in L2 then; everything else passes through once per evaluation and should not push them out
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
   const double* mats = ts_item_mats<M>(pb, item, np);
   const double* psrc = mats ? mats + msz + fwd : nullptr;   // pass 0: m of component 0, forward
   active = active && psrc != nullptr;
@@ -265,12 +268,12 @@ __device__ void ts_producer(const FastScratch<M, NP>& S, const magi_problem_t& p
       const uint32_t bar = bars + 8 * slot, dst = ring + slot * (uint32_t)(cw * 512);
       mbar_arrive_expect_tx(bar, (uint32_t)nt * 512);
       if (kind != 2) {
-        bulk_g2s(dst, psrc, (uint32_t)nt * 512, bar);
+        bulk_g2s_hint(dst, psrc, (uint32_t)nt * 512, bar, kind == 0 ? pol_keep : pol_stream);
         psrc += (ptrdiff_t)nt * 64;
       } else {
 #pragma unroll 1
         for (int i = 0; i < nt; ++i) {
-          bulk_g2s(dst + i * 512, psrc, 512, bar);
+          bulk_g2s_hint(dst + i * 512, psrc, 512, bar, pol_stream);
           psrc += (ptrdiff_t)nblk * 64;
         }
       }
