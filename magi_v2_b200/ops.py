@@ -363,8 +363,10 @@ class HostPipeline:
     `inputs(c)` / `outputs(c)` are views into the pinned blocks: fill / read them in place.  `run()` returns when
     every output block is complete on the host."""
 
-    def __init__(self, prob: "PosteriorProblem", R: int, n_chunks: int, n_streams: int):
-        self.prob, self.R, self.key = prob, R, (R, n_chunks, n_streams)
+    def __init__(self, prob: "PosteriorProblem", R: int, n_chunks: int, n_streams: int, ws_slot0: int = 1):
+        # ws_slot0: first workspace slot of this pipeline (two pipelines that run concurrently -- double buffering:
+        # one uploads / evaluates batch k+1 while the other still downloads batch k -- must not share scratch)
+        self.prob, self.R, self.key, self.ws_slot0 = prob, R, (R, n_chunks, n_streams), ws_slot0
         B, n, D, P = prob.B, prob.n, prob.D, prob.P
         n_chunks = max(1, min(n_chunks, B))
         per = -(-B // n_chunks)
@@ -435,7 +437,7 @@ class HostPipeline:
                     self.d_in[o0:o1].copy_(self.h_in[o0:o1], non_blocking=True)           # one H2D
                     dX, ds, dt, dbt = self._views(self.d_in, o0, self.shapes(b1 - b0))
                     lp, gX, gs, gt = self._views(self.d_out, o0, self.oshapes(b1 - b0))
-                    ws, nb = prob.workspace(R, slot=1 + c % len(self.streams), n_datasets=per)
+                    ws, nb = prob.workspace(R, slot=self.ws_slot0 + c % len(self.streams), n_datasets=per)
                     pb = prob.struct(R, b0, b1)
                     st = lib().magi_b200_logpost_grad(C.byref(pb), _ptr(dX), _ptr(ds), _ptr(dt), _ptr(dbt), _ptr(lp),
                                                       _ptr(gX), _ptr(gs), _ptr(gt), _ptr(ws), nb,
