@@ -602,7 +602,14 @@ def run_b200(args):
         samples = B * R * world * args.hmc_iters * hsteps
         # end to end: chain states up from pinned host memory, transitions, theta/sigma samples and the
         # final states back down; with world > 1 the theta samples are all-gathered (the one collective)
-        last = {}
+        last, pinned = {}, {}
+
+        def to_pinned(name, t):
+            """device -> a pinned host buffer kept across calls (a pageable `.cpu()` runs at a third of the link)"""
+            if name not in pinned or pinned[name].shape != t.shape:
+                pinned[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            pinned[name].copy_(t, non_blocking=True)
+            return pinned[name]
 
         def hmc_e2e():
             Xe, se, te = hX.to(dev, non_blocking=True), hs.to(dev, non_blocking=True), ht.to(dev, non_blocking=True)
@@ -610,7 +617,9 @@ def run_b200(args):
                               seed=1 + rank, chain_id0=rank * B * R, fixed_beta_temp=0.37)
             last["th"] = o["thetas_samps"]
             ths = gather_samples(o["thetas_samps"]) if world > 1 else o["thetas_samps"]
-            return ths.to("cpu", non_blocking=False), o["sigma_sqs_samps"].cpu(), Xe.cpu()
+            res = to_pinned("th", ths), to_pinned("sig", o["sigma_sqs_samps"]), to_pinned("X", Xe)
+            torch.cuda.synchronize()          # the host buffers are complete
+            return res
 
         ms_hmc_e2e = timed(hmc_e2e, hsteps, 3)
         hmc = {"samples_per_s": samples / (ms_hmc * 1e-3), "n_leapfrog": L, "transitions_per_launch": args.hmc_iters,
