@@ -263,3 +263,22 @@ def test_fast_path_edge_shapes(N, disc, band, cuda_device):
             assert relerr(gX[b, r], o[1]) <= TOL
             assert relerr(gs[b, r], o[2]) <= TOL
             assert relerr(gt[b, r], o[3]) <= TOL
+
+
+def test_fast_path_sirw_at_the_reference_grid(cuda_device):
+    """SIRW (D = 4, P = 5) at n = 161, band 80: the larger per-chain scalar area leaves the tile rings less room than
+    SEIR4 has, so the ring plan caps the chunk size and the long rows take four chunks per pass instead of three."""
+    model, R = "sirw", 8
+    rng = np.random.default_rng(42)
+    c = synth_constants(model, seed=3, N=21, disc=3, band=80, T=4.0, nan_frac=0.3)
+    assert c.I.shape[0] == 161
+    prob = device_problem([c], model, cuda_device)
+    X, s, tau = random_state(c, model, rng, R)
+    bt = rng.uniform(0.2, 1.2, (1, R))
+    lp, gX, gs, gt = _run(prob, X[None], s[None], tau[None], bt, cuda_device, "cta")
+    for r in (0, 5):
+        o = mo.log_posterior_and_grad_autograd(X[r], s[r], tau[r], bt[0, r], c)
+        assert abs(lp[0, r] - o[0]) <= TOL * abs(o[0])
+        assert relerr(gX[0, r], o[1]) <= TOL
+        assert relerr(gs[0, r], o[2]) <= TOL
+        assert relerr(gt[0, r], o[3]) <= TOL
