@@ -23,7 +23,7 @@
 
 namespace {
 
-constexpr int kW = 8, kT = 32 * kW, kCh = 8;
+constexpr int kCh = 8;   // chains per group (DMMA n = 8); the warps per CTA are a template parameter (KW: 8, 16 or 24)
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -34,6 +34,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 struct Geo {
   int np, nblk, kb, rbpc, nchunk, G;  // padded n, 8-row blocks, band in blocks (<0: dense), block rows per CTA, CTAs per column of the grid, chain groups
   int NG, GS;                         // chain groups per CTA (1 or 2: they share every matrix tile the CTA loads), CTAs per (chunk, d, b) = ceil(G / NG)
+  int KW;                             // warps per CTA of the three passes
   size_t per_bg;                      // workspace doubles per (dataset, chain group)
 };
 
@@ -50,19 +51,29 @@ Geo make_geo(const magi_problem_t* pb, int sms) {
   g.nblk = g.np / 8;
   g.kb = pb->band < 0 ? -1 : (pb->band + 7) >> 3;
   g.G = (pb->R + kCh - 1) / kCh;
+  // Warps per CTA.  The passes are bound by the latency of their tile loads (mostly L2 hits: the chain groups of a
+  // dataset read the same tiles at the same time) and a CTA's shared memory is one vector array whatever its size, so
+  // large grids take more warps per CTA: measured at n = 1281 (Lorenz-96, 2 x 64 chains) 1.90 / 1.33 / 1.18 / 1.34 ms
+  // per sweep with 8 / 16 / 24 / 32 warps; at n = 321 1.56 / 1.54 / 1.70; at n = 161 with 20 datasets 60 / 79 / 109 us.
+  g.KW = g.np >= 1024 ? 24 : (g.np >= 320 ? 16 : 8);
+  if (const char* f = getenv("MAGI_WIDE_KW")) {   // experiment knob
+    const int v = atoi(f);
+    if (v == 8 || v == 16 || v == 24) g.KW = v;
+  }
   // Chain groups per CTA.  2 = every matrix tile loaded once per 16 chains instead of once per 8 -- measured SLOWER at
   // the shape it was meant for (Lorenz-96, n = 1281, R = 64: 2.24 ms against 1.59 ms per evaluation sweep): two vector
   // arrays are 165 KB of shared memory, i.e. one CTA of 8 warps per SM instead of two, and the register-streamed tile
   // loads lose their latency cover.  Kept behind MAGI_WIDE_NG=2 for experiments; tests cover both.
   g.NG = 1;
   if (const char* f = getenv("MAGI_WIDE_NG")) {
-    if (f[0] == '2' && g.G >= 2 && (2 * (size_t)g.np * kCh + kW * 4 * 32 + 2 * kCh * pb->P) * sizeof(double) <= 200 * 1024)
+    if (f[0] == '2' && g.KW == 8 && g.G >= 2 &&
+        (2 * (size_t)g.np * kCh + 8 * 4 * 32 + 2 * kCh * pb->P) * sizeof(double) <= 200 * 1024)
       g.NG = 2;
   }
   g.GS = (g.G + g.NG - 1) / g.NG;
   const long ctas1 = (long)g.nblk * pb->D * pb->B * g.GS;      // with one block row per CTA
   long r = ctas1 / (4L * sms);
-  g.rbpc = (int)(r < 1 ? 1 : (r > 8 ? 8 : r));
+  g.rbpc = (int)(r < 1 ? 1 : (r > g.KW ? g.KW : r));
   g.nchunk = (g.nblk + g.rbpc - 1) / g.rbpc;
   g.per_bg = off_th(g, pb->D) + (size_t)g.nblk * pb->P * kCh;
   return g;
@@ -78,7 +89,7 @@ __device__ __forceinline__ void jrange(const Geo& g, int I, int& lo, int& hi) {
 }
 
 // cross-warp sum of NV values per lane; result valid in warp 0
-template <int NV>
+template <int NV, int KW>
 __device__ __forceinline__ void cta_reduce(double (&v)[NV], double* red) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __syncthreads();  // red free (previous block row consumed)
@@ -90,7 +101,7 @@ __device__ __forceinline__ void cta_reduce(double (&v)[NV], double* red) {
     for (int q = 0; q < NV; ++q) {
       double s = 0.0;
 #pragma unroll
-      for (int w = 0; w < kW; ++w) s += red[(w * NV + q) * 32 + lane];
+      for (int w = 0; w < KW; ++w) s += red[(w * NV + q) * 32 + lane];
       v[q] = s;
     }
   }
@@ -124,18 +135,18 @@ struct Args {
 // tiles -- no barrier and no reduction inside the loop.
 #define MAGI_WIDE_ROWS(I)                                                   \
   const int I0 = chunk * g.rbpc, I1 = min(g.nblk, I0 + g.rbpc);             \
-  for (int I = ROWW ? I0 + warp : I0; I < I1; I += ROWW ? kW : 1)
+  for (int I = ROWW ? I0 + warp : I0; I < I1; I += ROWW ? KW : 1)
 
 // ---- pass 1: u = S_C x_c, v = m x_c, r = f - v, t1 ------------------------------------------------------------
-template <class M, bool ROWW, int NG>
-__global__ void __launch_bounds__(kT) wide_pass1(Args a) {
+template <class M, bool ROWW, int NG, int KW>
+__global__ void __launch_bounds__(32 * KW) wide_pass1(Args a) {
   extern __shared__ double sm[];
-  constexpr int D = M::D, P = M::P;
+  constexpr int D = M::D, P = M::P, kT = 32 * KW;
   const Geo& g = a.g;
   const size_t vsz = (size_t)g.np * kCh;
   double* vs = sm;                          // [NG][np][8]
-  double* red = vs + NG * vsz;              // [kW][4][32]
-  double* ths = red + kW * 4 * 32;          // [NG][8][P]
+  double* red = vs + NG * vsz;              // [KW][4][32]
+  double* ths = red + KW * 4 * 32;          // [NG][8][P]
   // the chain groups of a dataset are adjacent in launch order: they read the same matrix rows at the same time (L2 hits)
   const int grp0 = (blockIdx.x % g.GS) * NG, chunk = blockIdx.x / g.GS, d = blockIdx.y, b = blockIdx.z;
   const int n = a.pb.n, R = a.pb.R, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -161,7 +172,7 @@ __global__ void __launch_bounds__(kT) wide_pass1(Args a) {
 #pragma unroll
     for (int g2 = 0; g2 < NG; ++g2) c[g2][0] = c[g2][1] = c[g2][2] = c[g2][3] = 0.0;
 #pragma unroll 4
-    for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : kW) {
+    for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : KW) {
       const size_t t = ((size_t)I * g.nblk + J) * 64;
       const int e0 = magi_tile_pos(lane >> 2, lane & 3), e1 = magi_tile_pos(lane >> 2, 4 + (lane & 3));
       const double a0 = matC[t + e0], a1 = matC[t + e1], m0 = matM[t + e0], m1 = matM[t + e1];
@@ -178,7 +189,7 @@ __global__ void __launch_bounds__(kT) wide_pass1(Args a) {
 #pragma unroll
     for (int g2 = 0; g2 < NG; ++g2) {
       const int grp = grp0 + g2;
-      if (!ROWW) cta_reduce<4>(c[g2], red);
+      if (!ROWW) cta_reduce<4, KW>(c[g2], red);
       if ((ROWW || warp == 0) && grp < g.G) {
         double* wsb = a.ws + (size_t)(b * g.G + grp) * g.per_bg;
         double* Rr = wsb + off_R(g, D);
@@ -211,9 +222,10 @@ __global__ void __launch_bounds__(kT) wide_pass1(Args a) {
 }
 
 // ---- pass 2: q = S_K r, t2 ---------------------------------------------------------------------------------------
-template <bool ROWW, int NG>
-__global__ void __launch_bounds__(kT) wide_pass2(Args a, int D) {
+template <bool ROWW, int NG, int KW>
+__global__ void __launch_bounds__(32 * KW) wide_pass2(Args a, int D) {
   extern __shared__ double sm[];
+  constexpr int kT = 32 * KW;
   const Geo& g = a.g;
   const size_t vsz = (size_t)g.np * kCh;
   double* vs = sm;                          // [NG][np][8]
@@ -235,7 +247,7 @@ __global__ void __launch_bounds__(kT) wide_pass2(Args a, int D) {
 #pragma unroll
     for (int g2 = 0; g2 < NG; ++g2) c[g2][0] = c[g2][1] = 0.0;
 #pragma unroll 8
-    for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : kW) {
+    for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : KW) {
       const size_t t = ((size_t)I * g.nblk + J) * 64;
       const double a0 = matK[t + magi_tile_pos(lane >> 2, lane & 3)], a1 = matK[t + magi_tile_pos(lane >> 2, 4 + (lane & 3))];
 #pragma unroll
@@ -248,7 +260,7 @@ __global__ void __launch_bounds__(kT) wide_pass2(Args a, int D) {
 #pragma unroll
     for (int g2 = 0; g2 < NG; ++g2) {
       const int grp = grp0 + g2;
-      if (!ROWW) cta_reduce<2>(c[g2], red);
+      if (!ROWW) cta_reduce<2, KW>(c[g2], red);
       if ((ROWW || warp == 0) && grp < g.G) {
         double* wsb = a.ws + (size_t)(b * g.G + grp) * g.per_bg;
         double* Q = wsb + off_Q(g, D) + (size_t)d * vsz;
@@ -267,15 +279,15 @@ __global__ void __launch_bounds__(kT) wide_pass2(Args a, int D) {
 }
 
 // ---- pass 3: m^T q and the point-wise assembly of dX; SSE and d/d theta partial sums -------------------------------
-template <class M, bool ROWW, int NG>
-__global__ void __launch_bounds__(kT) wide_pass3(Args a) {
+template <class M, bool ROWW, int NG, int KW>
+__global__ void __launch_bounds__(32 * KW) wide_pass3(Args a) {
   extern __shared__ double sm[];
-  constexpr int D = M::D, P = M::P;
+  constexpr int D = M::D, P = M::P, kT = 32 * KW;
   const Geo& g = a.g;
   const size_t vsz = (size_t)g.np * kCh;
   double* vs = sm;                          // [NG][np][8]
   double* red = vs + NG * vsz;
-  double* ths = red + kW * 4 * 32;          // [NG][8][P]
+  double* ths = red + KW * 4 * 32;          // [NG][8][P]
   // the chain groups of a dataset are adjacent in launch order: they read the same matrix rows at the same time (L2 hits)
   const int grp0 = (blockIdx.x % g.GS) * NG, chunk = blockIdx.x / g.GS, d = blockIdx.y, b = blockIdx.z;
   const int n = a.pb.n, R = a.pb.R, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -306,7 +318,7 @@ __global__ void __launch_bounds__(kT) wide_pass3(Args a) {
 #pragma unroll
     for (int g2 = 0; g2 < NG; ++g2) c[g2][0] = c[g2][1] = 0.0;
 #pragma unroll 8
-    for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : kW) {
+    for (int J = ROWW ? lo : lo + warp; J <= hi; J += ROWW ? 1 : KW) {
       // (m^T)(I, J) = tile (J, I) transposed: A[row][k] = tile[k][row]
       const size_t t = ((size_t)J * g.nblk + I) * 64;
       const double a0 = matM[t + magi_tile_pos(lane & 3, lane >> 2)], a1 = matM[t + magi_tile_pos(4 + (lane & 3), lane >> 2)];
@@ -320,7 +332,7 @@ __global__ void __launch_bounds__(kT) wide_pass3(Args a) {
 #pragma unroll
     for (int g2 = 0; g2 < NG; ++g2) {
       const int grp = grp0 + g2;
-      if (!ROWW) cta_reduce<2>(c[g2], red);
+      if (!ROWW) cta_reduce<2, KW>(c[g2], red);
       if ((ROWW || warp == 0) && grp < g.G) {
         double* wsb = a.ws + (size_t)(b * g.G + grp) * g.per_bg;
         const double* Qall = wsb + off_Q(g, D);
@@ -370,7 +382,7 @@ __global__ void __launch_bounds__(kT) wide_pass3(Args a) {
 // ---- final: per chain sums of the partials -> lp, d/d sigma_pre, d/d theta_pre --------------------------------------
 // One CTA per (dataset, chain group), one warp per chain: the lanes stride over the per-block-row partial sums and
 // combine them by shuffles (fixed order: deterministic).
-__global__ void __launch_bounds__(kT) wide_final(Args a, int D, int P) {
+__global__ void __launch_bounds__(32 * kCh) wide_final(Args a, int D, int P) {   // one warp per chain of a group
   const Geo& g = a.g;
   const int bg = blockIdx.x, ch = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = bg / g.G, r = (bg % g.G) * kCh + ch;
@@ -412,30 +424,36 @@ int sm_count() {
   return sms;
 }
 
-template <class M, bool ROWW, int NG>
+template <class M, bool ROWW, int NG, int KW>
 int launch_wide_t(const Args& a, cudaStream_t st) {
   const Geo& g = a.g;
   const dim3 grid(g.nchunk * g.GS, M::D, a.pb.B);
   if (grid.z > 65535) return MAGI_ERR_UNSUPPORTED;
-  const size_t smem = (NG * (size_t)g.np * kCh + kW * 4 * 32 + NG * kCh * M::P) * sizeof(double);
+  const size_t smem = (NG * (size_t)g.np * kCh + KW * 4 * 32 + NG * kCh * M::P) * sizeof(double);
   if (smem > 200 * 1024) return MAGI_ERR_UNSUPPORTED;
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(wide_pass1<M, ROWW, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
-  if ((e = cudaFuncSetAttribute(wide_pass2<ROWW, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
-  if ((e = cudaFuncSetAttribute(wide_pass3<M, ROWW, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
-  wide_pass1<M, ROWW, NG><<<grid, kT, smem, st>>>(a);
-  wide_pass2<ROWW, NG><<<grid, kT, smem, st>>>(a, M::D);
-  wide_pass3<M, ROWW, NG><<<grid, kT, smem, st>>>(a);
-  wide_final<<<a.pb.B * g.G, kT, 0, st>>>(a, M::D, M::P);
+  if ((e = cudaFuncSetAttribute(wide_pass1<M, ROWW, NG, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
+  if ((e = cudaFuncSetAttribute(wide_pass2<ROWW, NG, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
+  if ((e = cudaFuncSetAttribute(wide_pass3<M, ROWW, NG, KW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return magi_cuda_status(e);
+  wide_pass1<M, ROWW, NG, KW><<<grid, 32 * KW, smem, st>>>(a);
+  wide_pass2<ROWW, NG, KW><<<grid, 32 * KW, smem, st>>>(a, M::D);
+  wide_pass3<M, ROWW, NG, KW><<<grid, 32 * KW, smem, st>>>(a);
+  wide_final<<<a.pb.B * g.G, 32 * kCh, 0, st>>>(a, M::D, M::P);
   return magi_cuda_status(cudaGetLastError());
+}
+
+template <class M, int NG, int KW>
+int launch_wide_k(const Args& a, cudaStream_t st) {
+  const char* force = getenv("MAGI_WIDE_ROWW");   // experiment knob: 0 / 1 overrides the choice of work split
+  const bool roww = force ? (force[0] == '1' && a.g.rbpc <= KW) : a.g.rbpc == KW;
+  return roww ? launch_wide_t<M, true, NG, KW>(a, st) : launch_wide_t<M, false, NG, KW>(a, st);
 }
 
 template <class M>
 int launch_wide(const Args& a, cudaStream_t st) {
-  const char* force = getenv("MAGI_WIDE_ROWW");   // experiment knob: 0 / 1 overrides the choice of work split
-  const bool roww = force ? (force[0] == '1' && a.g.rbpc <= kW) : a.g.rbpc == kW;
-  if (a.g.NG == 2) return roww ? launch_wide_t<M, true, 2>(a, st) : launch_wide_t<M, false, 2>(a, st);
-  return roww ? launch_wide_t<M, true, 1>(a, st) : launch_wide_t<M, false, 1>(a, st);
+  if (a.g.KW == 24) return launch_wide_k<M, 1, 24>(a, st);
+  if (a.g.KW == 16) return launch_wide_k<M, 1, 16>(a, st);
+  return a.g.NG == 2 ? launch_wide_k<M, 2, 8>(a, st) : launch_wide_k<M, 1, 8>(a, st);
 }
 
 int model_dims(int id, int& D, int& P) {
